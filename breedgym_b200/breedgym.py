@@ -1,0 +1,186 @@
+"""Single-environment Gymnasium surface (drop-in for `breedgym:BreedGym`).
+
+Mirrors breedgym/breedgym.py:23-242 of the reference: same constructor
+arguments, spaces, `reset`/`step` contract, caching of `GEBV` / `corrcoef` by
+object identity, and reward rule.  The population is a device-resident
+`PackedPopulation`; `population[action]` is a lazy view and `simulator.cross`
+fuses the parent gather into the meiosis kernel.
+"""
+from __future__ import annotations
+
+from math import ceil, floor, sqrt
+from pathlib import Path
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import pandas as pd
+
+from .gym_compat import Env, spaces
+from .population import PackedPopulation
+from .simulator import Simulator
+from .utils.paths import DATA_PATH
+
+GENOME_FILE = DATA_PATH.joinpath("small_geno.npy")
+
+
+class BreedGym(Env):
+
+    metadata = {"render_modes": ["matplotlib"], "render_fps": 1}
+
+    def __init__(
+        self,
+        initial_population: Union[str, Path, np.ndarray, PackedPopulation] = GENOME_FILE,
+        num_generations: int = 10,
+        reward_shaping: bool = False,
+        render_mode: Optional[str] = None,
+        render_kwargs: Optional[dict] = None,
+        **kwargs,
+    ):
+        self.simulator = Simulator(**kwargs)
+        if isinstance(initial_population, (str, Path)):
+            germplasm = self.simulator.load_population(initial_population)
+        else:
+            germplasm = self.simulator.as_packed(initial_population)
+        self.device = self.simulator.device
+        self.germplasm = germplasm
+
+        self.num_generations = num_generations
+        self.reward_shaping = reward_shaping
+
+        self._population = None
+        self._GEBV, self._GEBV_cache = None, False
+        self._corrcoef, self._corrcoef_cache = None, False
+        self._set_spaces(self.germplasm.shape)
+
+        self.step_idx = None
+        self.episode_idx = -1
+        self.render_mode = render_mode
+        if self.render_mode is not None:
+            self.render_kwargs = dict(render_kwargs or {})
+            self.render_kwargs.setdefault("colors", ["b", "g", "r", "c", "m"])
+            self.render_kwargs.setdefault("offset", 0)
+            self.render_kwargs.setdefault("traits", self.simulator.trait_names)
+            self.render_kwargs.setdefault("other_features", [lambda: self.corrcoef])
+            self.render_kwargs.setdefault("feature_names", ["corrcoef"])
+            self.render_kwargs.setdefault("episode_names", "Episode {:d}")
+            self.axs = self._make_axs()
+
+    # ---- spaces ------------------------------------------------------------------
+    def _set_spaces(self, shape):
+        n = shape[0]
+        self.observation_space = spaces.Box(0, 1, shape=shape, dtype=np.bool_)
+        self.action_space = spaces.Sequence(spaces.Tuple((spaces.Discrete(n), spaces.Discrete(n))))
+
+    def _update_spaces(self):
+        self._set_spaces(self.population.shape)
+
+    # ---- gym API -----------------------------------------------------------------
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        super().reset(seed=seed)
+        if seed is not None:
+            self.simulator.set_seed(seed=seed)
+
+        self.step_idx = 0
+        self.episode_idx += 1
+        if options is not None and "n_individuals" in options.keys():
+            selected = self.np_random.choice(len(self.germplasm), options["n_individuals"], replace=False)
+            self.population = self.germplasm[selected]
+        else:
+            self.population = self.germplasm
+
+        self._update_spaces()
+        info = self._get_info()
+        if self.render_mode is not None:
+            self._render_step(info)
+        return self.population, info
+
+    def step(self, action):
+        """`action`: int array `n x 2`, one (parent, parent) index pair per cross."""
+        action = np.asarray(action)
+        if action.ndim != 2 or action.shape[1] != 2:
+            raise ValueError(f"action must have shape (n, 2), got {action.shape}")
+        parents = self.population[action]  # lazy n x 2 x markers x 2 view
+        self.population = self.simulator.cross(parents)
+        self.step_idx += 1
+        self._update_spaces()
+
+        info = self._get_info()
+        if self.render_mode is not None:
+            self._render_step(info)
+
+        truncated = self.step_idx == self.num_generations
+        if self.reward_shaping or truncated:
+            reward = np.mean(self.GEBV.to_numpy())
+        else:
+            reward = 0
+        return self.population, reward, False, truncated, info
+
+    def _get_info(self):
+        return {"GEBV": self.GEBV}
+
+    @property
+    def population(self):
+        return self._population
+
+    @population.setter
+    def population(self, new_pop):
+        self._population = new_pop
+        self._GEBV_cache = False
+        self._corrcoef_cache = False
+
+    @property
+    def GEBV(self) -> pd.DataFrame:
+        """GEBV of every individual for every trait (`n x t` DataFrame), cached per population."""
+        if not self._GEBV_cache:
+            self._GEBV = self.simulator.GEBV(self.population)
+            self._GEBV_cache = True
+        return self._GEBV
+
+    @property
+    def corrcoef(self):
+        if not self._corrcoef_cache:
+            self._corrcoef = self.simulator.corrcoef(self.population)
+            self._corrcoef_cache = True
+        return self._corrcoef
+
+    # ---- rendering (matplotlib is optional; imported lazily) ---------------------
+    def _plt(self):
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError as e:  # pragma: no cover
+            raise ImportError("render_mode='matplotlib' needs matplotlib") from e
+        return plt
+
+    def _make_axs(self):
+        if "axs" in self.render_kwargs:
+            return self.render_kwargs["axs"]
+        n_figs = len(self.render_kwargs["traits"]) + len(self.render_kwargs["other_features"])
+        nrows = floor(sqrt(n_figs))
+        ncols = ceil(n_figs / nrows)
+        axs = self._plt().subplots(nrows, ncols, figsize=(4 * ncols, 4 * nrows))[1]
+        return np.asarray(axs).flatten()
+
+    def _render_step(self, info: dict):
+        plt = self._plt()
+        color = self.render_kwargs["colors"][self.episode_idx % len(self.render_kwargs["colors"])]
+        series = [info["GEBV"][t] for t in self.render_kwargs["traits"]]
+        series += [f() for f in self.render_kwargs["other_features"]]
+        for ax, values in zip(self.axs, series):
+            bp = ax.boxplot(values, positions=[self.step_idx + self.episode_idx / 6], flierprops={"markersize": 2})
+            plt.setp(bp.values(), color=color)
+
+    def render(self, file_name: Optional[Union[str, Path]] = None):
+        if self.render_mode is None:
+            return
+        plt = self._plt()
+        xticks = np.arange(self.step_idx + 1)
+        titles = list(self.render_kwargs["traits"]) + list(self.render_kwargs["feature_names"])
+        for ax, title in zip(self.axs, titles):
+            ax.set_xticks(xticks + self.episode_idx / 12, xticks)
+            ax.set_title(title)
+            ax.grid(axis="y")
+            ax.set_xlabel("Generations [Years]")
+        plt.tight_layout()
+        if file_name is not None:
+            plt.savefig(file_name, bbox_inches="tight")
+        plt.show()

@@ -1,0 +1,349 @@
+// C-ABI entry points of libbreedgym_b200 (see include/breedgym_b200.h).
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "bg_internal.h"
+#include "threefry.cuh"
+
+static thread_local std::string g_err;
+
+void bg_set_error(const std::string &msg) { g_err = msg; }
+
+int bg_cuda_fail(cudaError_t e, const char *what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? BG_ENOMEM : BG_ECUDA;
+}
+
+int bg_reserve_u32(uint32_t **p, size_t *cap, size_t words)
+{
+    if (*cap >= words) return BG_OK;
+    if (*p) BG_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    BG_CUDA(cudaMalloc(p, words * sizeof(uint32_t)));
+    *cap = words;
+    return BG_OK;
+}
+
+int bg_reserve_acc(bg_engine *eng, size_t elems)
+{
+    if (eng->acc_cap >= elems) return BG_OK;
+    if (eng->d_acc) BG_CUDA(cudaFree(eng->d_acc));
+    eng->d_acc = nullptr;
+    eng->acc_cap = 0;
+    BG_CUDA(cudaMalloc(&eng->d_acc, elems * sizeof(unsigned long long)));
+    eng->acc_cap = elems;
+    return BG_OK;
+}
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+}  // namespace
+
+#define BG_ENTER(eng)                                                \
+    BG_REQUIRE((eng) != nullptr, BG_EINVAL, "null engine");          \
+    DeviceGuard guard__((eng)->device);                              \
+    BG_REQUIRE(guard__.ok, BG_ECUDA, "cudaSetDevice failed")
+
+extern "C" {
+
+int bg_version(void) { return BG_VERSION; }
+const char *bg_last_error(void) { return g_err.c_str(); }
+
+void bg_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t out[2])
+{
+    tf2x32(tf_make_key(k0, k1), x0, x1);
+    out[0] = x0;
+    out[1] = x1;
+}
+
+int bg_key_split(const uint32_t key[2], int64_t num, int layout, uint32_t *out)
+{
+    BG_REQUIRE(key && out && num >= 0, BG_EINVAL, "bg_key_split: bad argument");
+    BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
+    const TfKey k = tf_make_key(key[0], key[1]);
+    for (int64_t q = 0; q < num; ++q) {
+        const TfKey s = tf_split_at(k, (uint64_t)q, (uint64_t)num, layout);
+        out[2 * q] = s.k0;
+        out[2 * q + 1] = s.k1;
+    }
+    return BG_OK;
+}
+
+int bg_random_bits(const uint32_t key[2], int64_t n, int layout, uint32_t *out)
+{
+    BG_REQUIRE(key && out && n >= 0, BG_EINVAL, "bg_random_bits: bad argument");
+    BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
+    const TfKey k = tf_make_key(key[0], key[1]);
+    for (int64_t j = 0; j < n; ++j) out[j] = tf_bits_at(k, (uint64_t)j, (uint64_t)n, layout);
+    return BG_OK;
+}
+
+static inline uint32_t threshold_of(float r)
+{
+    // u = (bits>>9) * 2^-23 exactly, so  u < r  <=>  (bits>>9) < ceil(r * 2^23)
+    if (!(r > 0.0f)) return 0u;  // also NaN
+    const double t = ceil((double)r * 8388608.0);
+    return t >= 8388608.0 ? 8388608u : (uint32_t)t;
+}
+
+int bg_thresholds(const float *r, int64_t m, uint32_t *out)
+{
+    BG_REQUIRE(r && out && m >= 0, BG_EINVAL, "bg_thresholds: bad argument");
+    for (int64_t j = 0; j < m; ++j) out[j] = threshold_of(r[j]);
+    return BG_OK;
+}
+
+int64_t bg_words_per_row(int64_t n_markers) { return ((n_markers + 31) / 32 + 3) / 4 * 4; }
+
+int bg_engine_create(int device, bg_engine **out)
+{
+    BG_REQUIRE(out, BG_EINVAL, "null out pointer");
+    int count = 0;
+    BG_CUDA(cudaGetDeviceCount(&count));
+    BG_REQUIRE(device >= 0 && device < count, BG_EINVAL, "no such CUDA device");
+    DeviceGuard g(device);
+    BG_REQUIRE(g.ok, BG_ECUDA, "cudaSetDevice failed");
+    bg_engine *e = new (std::nothrow) bg_engine();
+    BG_REQUIRE(e, BG_ENOMEM, "out of host memory");
+    e->device = device;
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    *out = e;
+    return BG_OK;
+}
+
+static void free_map(bg_engine *e)
+{
+    cudaFree(e->d_thr);
+    cudaFree(e->d_wfix);
+    cudaFree(e->d_inv_scale);
+    cudaFree(e->d_wdig);
+    e->d_thr = nullptr;
+    e->d_wfix = nullptr;
+    e->d_inv_scale = nullptr;
+    e->d_wdig = nullptr;
+}
+
+int bg_engine_destroy(bg_engine *eng)
+{
+    if (!eng) return BG_OK;
+    {
+        DeviceGuard g(eng->device);
+        free_map(eng);
+        cudaFree(eng->d_mask);
+        cudaFree(eng->d_mut);
+        cudaFree(eng->d_acc);
+    }
+    delete eng;
+    return BG_OK;
+}
+
+int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects, int64_t n_markers, int32_t n_traits,
+                      float mutation)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(recomb && n_markers > 0 && n_markers < (int64_t(1) << 31) - 64, BG_EINVAL, "bad recombination vector");
+    BG_REQUIRE(n_traits >= 0 && (n_traits == 0 || effects), BG_EINVAL, "bad marker effects");
+    free_map(eng);
+    eng->m = n_markers;
+    eng->W = (int32_t)((n_markers + 31) / 32);
+    eng->Wpad = (int32_t)bg_words_per_row(n_markers);
+    eng->T = n_traits;
+    eng->mut_thr = threshold_of(mutation);
+
+    const size_t nthr = (size_t)eng->Wpad * 32 + 32;
+    std::vector<uint32_t> thr(nthr, 0u);
+    for (int64_t j = 0; j < n_markers; ++j) thr[j] = threshold_of(recomb[j]);
+    BG_CUDA(cudaMalloc(&eng->d_thr, nthr * sizeof(uint32_t)));
+    BG_CUDA(cudaMemcpy(eng->d_thr, thr.data(), nthr * sizeof(uint32_t), cudaMemcpyHostToDevice));
+
+    if (n_traits > 0) {
+        // fixed point: w_fix = rint(w * 2^s), s = largest shift with 2*sum|w| * 2^s < 2^61
+        const size_t stride = (size_t)((eng->Wpad + 7) / 8) * 256;
+        std::vector<long long> wfix(stride * n_traits, 0ll);
+        std::vector<double> inv(n_traits, 1.0);
+        for (int t = 0; t < n_traits; ++t) {
+            double sum = 0.0;
+            for (int64_t j = 0; j < n_markers; ++j) {
+                const double w = (double)effects[j * n_traits + t];
+                BG_REQUIRE(isfinite(w), BG_EINVAL, "marker effects must be finite");
+                sum += fabs(w);
+            }
+            int s = 0;
+            if (sum > 0.0) {
+                int ex;
+                frexp(2.0 * sum, &ex);  // 2*sum < 2^ex
+                s = 61 - ex;
+                if (s > 1000) s = 1000;
+                if (s < -1000) s = -1000;
+            }
+            for (int64_t j = 0; j < n_markers; ++j)
+                wfix[t * stride + j] = llrint(ldexp((double)effects[j * n_traits + t], s));
+            inv[t] = ldexp(1.0, -s);
+        }
+        BG_CUDA(cudaMalloc(&eng->d_wfix, wfix.size() * sizeof(long long)));
+        BG_CUDA(cudaMemcpy(eng->d_wfix, wfix.data(), wfix.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        BG_CUDA(cudaMalloc(&eng->d_inv_scale, n_traits * sizeof(double)));
+        BG_CUDA(cudaMemcpy(eng->d_inv_scale, inv.data(), n_traits * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return BG_OK;
+}
+
+int bg_pack(bg_engine *eng, const uint8_t *bool_in, uint32_t *packed_out, int64_t rows, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(eng->m > 0, BG_ESTATE, "engine has no map (call bg_engine_set_map)");
+    BG_REQUIRE(rows >= 0 && (rows == 0 || (bool_in && packed_out)), BG_EINVAL, "bg_pack: bad argument");
+    return bg_launch_pack(bool_in, packed_out, rows, eng->m, eng->W, eng->Wpad, (cudaStream_t)stream);
+}
+
+int bg_unpack(bg_engine *eng, const uint32_t *packed_in, uint8_t *bool_out, int64_t rows, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(eng->m > 0, BG_ESTATE, "engine has no map (call bg_engine_set_map)");
+    BG_REQUIRE(rows >= 0 && (rows == 0 || (packed_in && bool_out)), BG_EINVAL, "bg_unpack: bad argument");
+    return bg_launch_unpack(packed_in, bool_out, rows, eng->m, eng->Wpad, (cudaStream_t)stream);
+}
+
+int bg_gather_individuals(bg_engine *eng, const uint32_t *src, const int32_t *idx, uint32_t *dst, int64_t E, int64_t n_src,
+                          int64_t n, int64_t src_env_rows, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(eng->m > 0, BG_ESTATE, "engine has no map (call bg_engine_set_map)");
+    BG_REQUIRE(E >= 0 && n >= 0 && n_src > 0, BG_EINVAL, "bg_gather_individuals: bad shape");
+    BG_REQUIRE(E * n == 0 || (src && idx && dst), BG_EINVAL, "bg_gather_individuals: null buffer");
+    return bg_launch_gather(src, idx, dst, E, n_src, n, src_env_rows, eng->Wpad, (cudaStream_t)stream);
+}
+
+int bg_cross(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src, int64_t n,
+             const uint32_t cross_key[2], int layout, int schedule, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(E >= 0 && n >= 0 && n_src > 0 && cross_key, BG_EINVAL, "bg_cross: bad shape");
+    BG_REQUIRE(E * n == 0 || (pop && parents && out), BG_EINVAL, "bg_cross: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (E * n == 0) return BG_OK;
+    if (E == 1)
+        return bg_launch_meiosis_rows(eng, BG_ROWS_CROSS, 2 * n, cross_key, layout, schedule, nullptr, nullptr, pop, parents, n_src,
+                                      0, out, st);
+    const size_t words = (size_t)2 * n * eng->Wpad;
+    int rc = bg_reserve_u32(&eng->d_mask, &eng->mask_cap, words);
+    if (rc) return rc;
+    if (eng->mut_thr) {
+        rc = bg_reserve_u32(&eng->d_mut, &eng->mut_cap, words);
+        if (rc) return rc;
+    }
+    rc = bg_launch_meiosis_rows(eng, BG_ROWS_MASK, 2 * n, cross_key, layout, schedule, eng->d_mask,
+                                eng->mut_thr ? eng->d_mut : nullptr, nullptr, nullptr, 0, 0, nullptr, st);
+    if (rc) return rc;
+    return bg_launch_blend(eng, pop, parents, eng->d_mask, eng->mut_thr ? eng->d_mut : nullptr, out, E, n_src, n, st);
+}
+
+int bg_double_haploid(bg_engine *eng, const uint32_t *pop, uint32_t *out, int64_t n, int64_t n_offspring,
+                      const uint32_t cross_key[2], int layout, int schedule, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(n >= 0 && n_offspring >= 0 && cross_key, BG_EINVAL, "bg_double_haploid: bad shape");
+    if (n * n_offspring == 0) return BG_OK;
+    BG_REQUIRE(pop && out, BG_EINVAL, "bg_double_haploid: null buffer");
+    return bg_launch_meiosis_rows(eng, BG_ROWS_DH, n * n_offspring, cross_key, layout, schedule, nullptr, nullptr, pop, nullptr, n,
+                                  n_offspring, out, (cudaStream_t)stream);
+}
+
+int bg_meiosis_masks(bg_engine *eng, uint32_t *mask_out, int64_t rows, const uint32_t cross_key[2], int layout, int schedule,
+                     void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(rows >= 0 && cross_key && (rows == 0 || mask_out), BG_EINVAL, "bg_meiosis_masks: bad argument");
+    int rc = BG_OK;
+    if (eng->mut_thr) {
+        rc = bg_reserve_u32(&eng->d_mut, &eng->mut_cap, (size_t)rows * eng->Wpad);
+        if (rc) return rc;
+    }
+    return bg_launch_meiosis_rows(eng, BG_ROWS_MASK, rows, cross_key, layout, schedule, mask_out,
+                                  eng->mut_thr ? eng->d_mut : nullptr, nullptr, nullptr, 0, 0, nullptr, (cudaStream_t)stream);
+}
+
+int bg_gebv_algo(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, int algo, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(rows >= 0 && (rows == 0 || (pop && out)), BG_EINVAL, "bg_gebv: bad argument");
+    return bg_launch_gebv(eng, pop, rows, out, algo, (cudaStream_t)stream);
+}
+
+int bg_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, void *stream)
+{
+    return bg_gebv_algo(eng, pop, rows, out, 0, stream);
+}
+
+int bg_reduce_max(bg_engine *eng, const float *gebv, int64_t E, int64_t per_env, float *out, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(E >= 0 && (E == 0 || (gebv && out)), BG_EINVAL, "bg_reduce_max: bad argument");
+    return bg_launch_reduce(gebv, E, per_env, out, 0, (cudaStream_t)stream);
+}
+
+int bg_reduce_mean(bg_engine *eng, const float *gebv, int64_t E, int64_t per_env, float *out, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(E >= 0 && (E == 0 || (gebv && out)), BG_EINVAL, "bg_reduce_mean: bad argument");
+    return bg_launch_reduce(gebv, E, per_env, out, 1, (cudaStream_t)stream);
+}
+
+int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_total, int64_t env_begin, int64_t E, int64_t n_germ,
+                     int64_t n, int layout, int32_t *idx_out, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(random_key && E >= 0 && n >= 0 && n_germ > 0 && (E * n == 0 || idx_out), BG_EINVAL, "bg_reset_indices: bad argument");
+    BG_REQUIRE(env_begin >= 0 && env_begin + E <= E_total, BG_EINVAL, "bg_reset_indices: env range outside [0, E_total)");
+    return bg_launch_reset_indices(eng, random_key, E_total, env_begin, E, n_germ, n, layout, idx_out, (cudaStream_t)stream);
+}
+
+int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_t *actions_host, int32_t *actions_dev, int64_t E,
+                int64_t n_src, int64_t n, const uint32_t cross_key[2], int layout, int schedule, float *gebv_dev,
+                float *reward_dev, float *gebv_host, float *reward_host, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(actions_dev && gebv_dev, BG_EINVAL, "bg_vec_step: null device buffer");
+    BG_REQUIRE(!reward_host || reward_dev, BG_EINVAL, "bg_vec_step: reward_host needs reward_dev");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (actions_host)
+        BG_CUDA(cudaMemcpyAsync(actions_dev, actions_host, (size_t)E * n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    int rc = bg_cross(eng, pop, actions_dev, out, E, n_src, n, cross_key, layout, schedule, stream);
+    if (rc) return rc;
+    rc = bg_launch_gebv(eng, out, E * n, gebv_dev, 0, st);
+    if (rc) return rc;
+    if (reward_dev) {
+        rc = bg_launch_reduce(gebv_dev, E, n * eng->T, reward_dev, 0, st);
+        if (rc) return rc;
+    }
+    bool sync = false;
+    if (gebv_host) {
+        BG_CUDA(cudaMemcpyAsync(gebv_host, gebv_dev, (size_t)E * n * eng->T * sizeof(float), cudaMemcpyDeviceToHost, st));
+        sync = true;
+    }
+    if (reward_host) {
+        BG_CUDA(cudaMemcpyAsync(reward_host, reward_dev, (size_t)E * sizeof(float), cudaMemcpyDeviceToHost, st));
+        sync = true;
+    }
+    if (sync) BG_CUDA(cudaStreamSynchronize(st));
+    return BG_OK;
+}
+
+}  // extern "C"

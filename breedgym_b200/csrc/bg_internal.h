@@ -1,0 +1,71 @@
+// Internal declarations shared by the translation units of libbreedgym_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/breedgym_b200.h"
+
+struct bg_engine {
+    int device = 0;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    // map constants
+    int64_t m = 0;       // markers
+    int32_t W = 0;       // ceil(m/32)
+    int32_t Wpad = 0;    // W rounded up to a multiple of 4
+    int32_t T = 0;       // traits
+    uint32_t *d_thr = nullptr;        // [Wpad*32 + 32] recombination thresholds (zero padded)
+    uint32_t mut_thr = 0;             // mutation threshold (0 = off)
+    long long *d_wfix = nullptr;      // [T][Wpad*32] fixed-point effects (zero padded)
+    double *d_inv_scale = nullptr;    // [T] 2^-s_t
+    signed char *d_wdig = nullptr;    // [T*8][Kpad] int8 base-256 digits (tensor-core GEBV)
+    int64_t Kpad = 0;
+    // grow-only scratch
+    uint32_t *d_mask = nullptr;
+    uint32_t *d_mut = nullptr;
+    size_t mask_cap = 0, mut_cap = 0;   // words
+    unsigned long long *d_acc = nullptr;
+    size_t acc_cap = 0;                 // elements
+};
+
+void bg_set_error(const std::string &msg);
+int bg_cuda_fail(cudaError_t e, const char *what);
+
+#define BG_CUDA(call)                                       \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return bg_cuda_fail(e__, #call); \
+    } while (0)
+
+#define BG_REQUIRE(cond, code, msg) \
+    do {                            \
+        if (!(cond)) {              \
+            bg_set_error(msg);      \
+            return (code);          \
+        }                           \
+    } while (0)
+
+int bg_reserve_u32(uint32_t **p, size_t *cap, size_t words);
+int bg_reserve_acc(bg_engine *eng, size_t elems);
+
+// meiosis.cu
+enum { BG_ROWS_MASK = 0, BG_ROWS_CROSS = 1, BG_ROWS_DH = 2 };
+int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_t cross_key[2], int layout, int schedule,
+                           uint32_t *mask_out, uint32_t *mut_out, const uint32_t *pop, const int32_t *parents,
+                           int64_t n_src, int64_t dh_offspring, uint32_t *out, cudaStream_t st);
+int bg_launch_blend(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask,
+                    const uint32_t *mut, uint32_t *out, int64_t E, int64_t n_src, int64_t n, cudaStream_t st);
+
+// gebv.cu
+int bg_launch_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, int algo, cudaStream_t st);
+int bg_launch_reduce(const float *in, int64_t E, int64_t per_env, float *out, int op, cudaStream_t st);
+
+// layout.cu
+int bg_launch_pack(const uint8_t *in, uint32_t *out, int64_t rows, int64_t m, int W, int Wpad, cudaStream_t st);
+int bg_launch_unpack(const uint32_t *in, uint8_t *out, int64_t rows, int64_t m, int Wpad, cudaStream_t st);
+int bg_launch_gather(const uint32_t *src, const int32_t *idx, uint32_t *dst, int64_t E, int64_t n_src, int64_t n,
+                     int64_t src_env_rows, int Wpad, cudaStream_t st);
+int bg_launch_reset_indices(bg_engine *eng, const uint32_t key[2], int64_t E_total, int64_t env_begin, int64_t E, int64_t N,
+                            int64_t n, int layout, int32_t *idx_out, cudaStream_t st);

@@ -1,0 +1,358 @@
+// Meiosis / cross kernels (sm_100a).
+//
+// Replaces chromax functional.cross/_meiosis as called from
+// breedgym/breedgym.py:142-143 and breedgym/vector/vec_env.py:75-77,89-91:
+//   u = uniform(key,(m,)); s = u < r; mask = cumulative XOR(s); hap[j] = ind[j, mask[j]]
+//
+// One CTA per gamete row q.  Lanes evaluate Threefry blocks, __ballot_sync packs 32
+// compare results into a recombination word held in shared memory (m/8 bytes per
+// row, <= 227 KB => m <= ~1.8 M markers), an in-word shift-XOR ladder plus a
+// ballot/popc warp scan and a block scan turn it into the crossover mask, and the
+// mask then either goes to global memory (vector env: masks are shared by all
+// envs, see blend_envs_kernel) or selects alleles from the two bit-plane rows of
+// the parent with 128-bit loads/stores (unique-key cross, double haploid).
+#include "bg_internal.h"
+#include "threefry.cuh"
+
+namespace {
+
+constexpr int ILP = 4;
+constexpr uint32_t FULL = 0xffffffffu;
+
+struct RowParams {
+    const uint32_t *thr;
+    uint32_t mut_thr;
+    uint32_t m, W, Wpad;
+    uint32_t k0, k1;
+    uint64_t rows;
+    int schedule;
+    int mode;
+    uint32_t *mask_out;
+    uint32_t *mut_out;
+    const uint32_t *pop;
+    const int32_t *parents;
+    int64_t n_src;
+    int64_t dh_offspring;
+    uint32_t *out;
+};
+
+template <int N>
+__device__ __forceinline__ void tf2x32_n(const TfKey &k, uint32_t (&x0)[N], uint32_t (&x1)[N])
+{
+#define BG_R(r)                                  \
+    _Pragma("unroll") for (int u = 0; u < N; ++u) \
+    {                                            \
+        x0[u] += x1[u];                          \
+        x1[u] = __funnelshift_l(x1[u], x1[u], r); \
+        x1[u] ^= x0[u];                          \
+    }
+#define BG_INJ(a, b, c)                          \
+    _Pragma("unroll") for (int u = 0; u < N; ++u) \
+    {                                            \
+        x0[u] += (a);                            \
+        x1[u] += (b) + (c);                      \
+    }
+    BG_INJ(k.k0, k.k1, 0u)
+    BG_R(13) BG_R(15) BG_R(26) BG_R(6) BG_INJ(k.k1, k.k2, 1u)
+    BG_R(17) BG_R(29) BG_R(16) BG_R(24) BG_INJ(k.k2, k.k0, 2u)
+    BG_R(13) BG_R(15) BG_R(26) BG_R(6) BG_INJ(k.k0, k.k1, 3u)
+    BG_R(17) BG_R(29) BG_R(16) BG_R(24) BG_INJ(k.k1, k.k2, 4u)
+    BG_R(13) BG_R(15) BG_R(26) BG_R(6) BG_INJ(k.k2, k.k0, 5u)
+#undef BG_R
+#undef BG_INJ
+}
+
+// Draw the m Bernoulli bits `uniform(key)[j] < thr[j]` of one row into the zeroed
+// shared bit array S (marker j -> bit j&31 of S[j>>5]).
+template <int LAYOUT, bool CONST_THR>
+__device__ __forceinline__ void draw_bits(uint32_t *S, const TfKey key, const uint32_t *__restrict__ thr,
+                                          uint32_t cthr, uint32_t m, uint32_t lane, uint32_t warp, uint32_t NW)
+{
+    if (LAYOUT == BG_LAYOUT_LEGACY) {
+        // block c yields draw c (word 0) and draw c+h (word 1): two bit streams, the
+        // second starting at bit offset h&31 of word h>>5.
+        const uint32_t h = (m + 1) >> 1, G = (h + 31) >> 5, sh = h & 31, wsB = h >> 5;
+        for (uint32_t g0 = warp * ILP; g0 < G; g0 += NW * ILP) {
+            uint32_t x0[ILP], x1[ILP], tA[ILP], tB[ILP];
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                const uint32_t c = (g0 + u) * 32 + lane, cB = c + h;
+                const bool vA = c < h, vB = vA && cB < m;
+                x0[u] = c;
+                x1[u] = vB ? cB : 0u;  // odd m: the last block's second counter is the zero pad
+                tA[u] = vA ? (CONST_THR ? cthr : __ldg(thr + c)) : 0u;
+                tB[u] = vB ? (CONST_THR ? cthr : __ldg(thr + cB)) : 0u;
+            }
+            tf2x32_n<ILP>(key, x0, x1);
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                const uint32_t g = g0 + u;
+                const uint32_t bA = __ballot_sync(FULL, (x0[u] >> 9) < tA[u]);
+                const uint32_t bB = __ballot_sync(FULL, (x1[u] >> 9) < tB[u]);
+                if (g < G) {
+                    if (lane == 0 && bA) atomicOr(&S[g], bA);
+                    if (lane == 1 && bB) atomicOr(&S[wsB + g], bB << sh);
+                    if (lane == 2 && sh && (bB >> (32 - sh))) atomicOr(&S[wsB + g + 1], bB >> (32 - sh));
+                }
+            }
+        }
+    } else {
+        const uint32_t G = (m + 31) >> 5;
+        for (uint32_t g0 = warp * ILP; g0 < G; g0 += NW * ILP) {
+            uint32_t x0[ILP], x1[ILP], tA[ILP];
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                const uint32_t c = (g0 + u) * 32 + lane;
+                x0[u] = 0u;
+                x1[u] = c;
+                tA[u] = (c < m) ? (CONST_THR ? cthr : __ldg(thr + c)) : 0u;
+            }
+            tf2x32_n<ILP>(key, x0, x1);
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                const uint32_t g = g0 + u;
+                const uint32_t b = __ballot_sync(FULL, ((x0[u] ^ x1[u]) >> 9) < tA[u]);
+                if (g < G && lane == 0) S[g] = b;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t inword_xor_scan(uint32_t x)
+{
+    x ^= x << 1;
+    x ^= x << 2;
+    x ^= x << 4;
+    x ^= x << 8;
+    x ^= x << 16;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+    uint32_t r;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ int64_t norm_index(int64_t a, int64_t n)
+{
+    if (a < 0) a += n;
+    a = a < 0 ? 0 : a;
+    return a > n - 1 ? n - 1 : a;
+}
+
+__device__ __forceinline__ uint4 blend4(uint4 h0, uint4 h1, uint4 M)
+{
+    uint4 o;
+    o.x = (h0.x & ~M.x) | (h1.x & M.x);
+    o.y = (h0.y & ~M.y) | (h1.y & M.y);
+    o.z = (h0.z & ~M.z) | (h1.z & M.z);
+    o.w = (h0.w & ~M.w) | (h1.w & M.w);
+    return o;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(1024) meiosis_rows_kernel(const RowParams P)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t wtot[32];
+    uint32_t *S = smem;
+    uint32_t *Mu = smem + (P.Wpad + 8);
+    const uint32_t tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
+    const uint64_t q = blockIdx.x;
+    const bool has_mut = P.mut_thr != 0;
+    const uint32_t W = P.W, Wpad = P.Wpad, m = P.m;
+
+    for (uint32_t i = tid; i < Wpad + 8; i += NT) {
+        S[i] = 0;
+        if (has_mut) Mu[i] = 0;
+    }
+    // per-gamete key: #q of split(k, rows); S2 splits it again into (rec, mut)
+    const TfKey kc = tf_make_key(P.k0, P.k1);
+    const TfKey kq = tf_split_at(kc, q, P.rows, LAYOUT);
+    TfKey krec = kq, kmut = kq;
+    if (P.schedule == BG_SCHEDULE_S2) {
+        krec = tf_split_at(kq, 0, 2, LAYOUT);
+        if (has_mut) kmut = tf_split_at(kq, 1, 2, LAYOUT);
+    }
+    __syncthreads();
+
+    draw_bits<LAYOUT, false>(S, krec, P.thr, 0u, m, lane, warp, NW);
+    if (has_mut) draw_bits<LAYOUT, true>(Mu, kmut, nullptr, P.mut_thr, m, lane, warp, NW);
+    __syncthreads();
+
+    // inclusive prefix-XOR over the whole row, in place: each warp owns a contiguous
+    // chunk (multiple of 32 words), then chunk parities are combined across warps.
+    const uint32_t CH = ((((W + NW - 1) / NW) + 31) >> 5) << 5;
+    const uint32_t wbeg = warp * CH, wend = min(W, wbeg + CH);
+    uint32_t carry = 0;
+    for (uint32_t w0 = wbeg; w0 < wend; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        uint32_t x = inword_xor_scan(w < wend ? S[w] : 0u);
+        const uint32_t b = __ballot_sync(FULL, x >> 31);
+        const uint32_t pre = (__popc(b & lanemask_lt()) & 1u) ^ carry;
+        x ^= 0u - pre;
+        carry ^= __popc(b) & 1u;
+        if (w < wend) S[w] = x;
+    }
+    if (lane == 0) wtot[warp] = carry;
+    __syncthreads();
+    {
+        const uint32_t v = (lane < warp) ? wtot[lane] : 0u;
+        const uint32_t cin = __popc(__ballot_sync(FULL, v)) & 1u;
+        const uint32_t tail = m & 31;
+        for (uint32_t w = wbeg + lane; w < wend; w += 32) {
+            uint32_t x = S[w] ^ (0u - cin);
+            if (w == W - 1 && tail) x &= (1u << tail) - 1u;  // keep padding bits zero
+            S[w] = x;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t W4 = Wpad >> 2;
+    const uint4 *S4 = reinterpret_cast<const uint4 *>(S);
+    const uint4 *Mu4 = reinterpret_cast<const uint4 *>(Mu);
+    if (P.mode == BG_ROWS_MASK) {
+        uint4 *mo = reinterpret_cast<uint4 *>(P.mask_out + q * Wpad);
+        for (uint32_t v = tid; v < W4; v += NT) mo[v] = S4[v];
+        if (has_mut) {
+            uint4 *uo = reinterpret_cast<uint4 *>(P.mut_out + q * Wpad);
+            for (uint32_t v = tid; v < W4; v += NT) uo[v] = Mu4[v];
+        }
+        return;
+    }
+    int64_t src;
+    uint4 *dst0, *dst1 = nullptr;
+    if (P.mode == BG_ROWS_CROSS) {
+        src = norm_index(P.parents[q], P.n_src);
+        dst0 = reinterpret_cast<uint4 *>(P.out + q * Wpad);
+    } else {  // double haploid: the gamete fills both planes of individual q
+        src = (int64_t)(q / (uint64_t)P.dh_offspring);
+        dst0 = reinterpret_cast<uint4 *>(P.out + (2 * q) * Wpad);
+        dst1 = dst0 + W4;
+    }
+    const uint4 *h0 = reinterpret_cast<const uint4 *>(P.pop + (uint64_t)(2 * src) * Wpad);
+    const uint4 *h1 = h0 + W4;
+    for (uint32_t v = tid; v < W4; v += NT) {
+        uint4 o = blend4(__ldg(h0 + v), __ldg(h1 + v), S4[v]);
+        if (has_mut) {
+            const uint4 u = Mu4[v];
+            o.x ^= u.x; o.y ^= u.y; o.z ^= u.z; o.w ^= u.w;
+        }
+        dst0[v] = o;
+        if (dst1) dst1[v] = o;
+    }
+}
+
+// Vector env: out[e][q] = blend(pop[e][parents[e][q]] planes, mask[q]) for all envs e.
+// The mask (and mutation) words are loaded once per thread and reused for every env.
+template <bool HAS_MUT>
+__global__ void __launch_bounds__(256) blend_envs_kernel(const uint4 *__restrict__ pop, const int32_t *__restrict__ parents,
+                                                         const uint4 *__restrict__ mask, const uint4 *__restrict__ mut,
+                                                         uint4 *__restrict__ out, int E, int64_t n_src, int64_t rows,
+                                                         int W4, int env_chunk)
+{
+    const int v = blockIdx.y * blockDim.x + threadIdx.x;
+    if (v >= W4) return;
+    const int64_t q = blockIdx.x;
+    const uint4 M = __ldg(mask + q * W4 + v);
+    uint4 U = make_uint4(0, 0, 0, 0);
+    if (HAS_MUT) U = __ldg(mut + q * W4 + v);
+    const int e0 = blockIdx.z * env_chunk, e1 = min(E, e0 + env_chunk);
+    constexpr int UN = 4;
+    for (int e = e0; e < e1; e += UN) {
+        uint4 a[UN], b[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (e + u < e1) {
+                const int64_t s = norm_index(__ldg(parents + (int64_t)(e + u) * rows + q), n_src);
+                const uint4 *h0 = pop + ((int64_t)(e + u) * n_src + s) * 2 * W4 + v;
+                a[u] = __ldg(h0);
+                b[u] = __ldg(h0 + W4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (e + u < e1) {
+                uint4 o = blend4(a[u], b[u], M);
+                if (HAS_MUT) {
+                    o.x ^= U.x; o.y ^= U.y; o.z ^= U.z; o.w ^= U.w;
+                }
+                out[((int64_t)(e + u) * rows + q) * W4 + v] = o;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_t cross_key[2], int layout, int schedule,
+                           uint32_t *mask_out, uint32_t *mut_out, const uint32_t *pop, const int32_t *parents,
+                           int64_t n_src, int64_t dh_offspring, uint32_t *out, cudaStream_t st)
+{
+    BG_REQUIRE(eng && eng->d_thr, BG_ESTATE, "engine has no map (call bg_engine_set_map)");
+    BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
+    BG_REQUIRE(schedule == BG_SCHEDULE_S1 || schedule == BG_SCHEDULE_S2, BG_EINVAL, "bad key schedule");
+    BG_REQUIRE(!(schedule == BG_SCHEDULE_S1 && eng->mut_thr), BG_EINVAL, "schedule S1 has no mutation key");
+    BG_REQUIRE(rows >= 0 && rows < (int64_t(1) << 31), BG_ELIMIT, "too many gamete rows");
+    if (rows == 0) return BG_OK;
+    const bool has_mut = eng->mut_thr != 0;
+    const size_t smem = (size_t)(eng->Wpad + 8) * 4 * (has_mut ? 2 : 1);
+    BG_REQUIRE(smem <= (size_t)eng->max_smem_optin, BG_ELIMIT,
+               "n_markers too large for the shared-memory row buffer (limit ~1.8M markers, half with mutation)");
+    RowParams P;
+    P.thr = eng->d_thr;
+    P.mut_thr = eng->mut_thr;
+    P.m = (uint32_t)eng->m;
+    P.W = (uint32_t)eng->W;
+    P.Wpad = (uint32_t)eng->Wpad;
+    P.k0 = cross_key[0];
+    P.k1 = cross_key[1];
+    P.rows = (uint64_t)rows;
+    P.schedule = schedule;
+    P.mode = mode;
+    P.mask_out = mask_out;
+    P.mut_out = mut_out;
+    P.pop = pop;
+    P.parents = parents;
+    P.n_src = n_src;
+    P.dh_offspring = dh_offspring > 0 ? dh_offspring : 1;
+    P.out = out;
+    const int NT = eng->W <= 1024 ? 256 : 1024;
+    auto kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE>;
+    if (smem > 48 * 1024) BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)rows, NT, smem, st>>>(P);
+    BG_CUDA(cudaGetLastError());
+    return BG_OK;
+}
+
+int bg_launch_blend(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask,
+                    const uint32_t *mut, uint32_t *out, int64_t E, int64_t n_src, int64_t n, cudaStream_t st)
+{
+    const int W4 = eng->Wpad / 4;
+    const int64_t rows = 2 * n;
+    if (rows == 0 || E == 0) return BG_OK;
+    BG_REQUIRE(E < (int64_t(1) << 31) && rows < (int64_t(1) << 31), BG_ELIMIT, "blend grid too large");
+    int threads = ((W4 + 31) / 32) * 32;
+    if (threads > 256) threads = 256;
+    const int tiles = (W4 + threads - 1) / threads;
+    BG_REQUIRE(tiles <= 65535, BG_ELIMIT, "n_markers too large for the blend grid");
+    // env chunk: enough CTAs for several waves, but >= 4 envs per CTA so the mask load is amortised
+    int chunk = 8;
+    if (const char *s = getenv("BG_BLEND_ENV_CHUNK")) chunk = atoi(s) > 0 ? atoi(s) : chunk;
+    int64_t zs = (E + chunk - 1) / chunk;
+    if (zs > 65535) {
+        chunk = (int)((E + 65534) / 65535);
+        zs = (E + chunk - 1) / chunk;
+    }
+    dim3 grid((unsigned)rows, (unsigned)tiles, (unsigned)zs);
+    if (mut)
+        blend_envs_kernel<true><<<grid, threads, 0, st>>>((const uint4 *)pop, parents, (const uint4 *)mask, (const uint4 *)mut,
+                                                          (uint4 *)out, (int)E, n_src, rows, W4, chunk);
+    else
+        blend_envs_kernel<false><<<grid, threads, 0, st>>>((const uint4 *)pop, parents, (const uint4 *)mask, nullptr,
+                                                           (uint4 *)out, (int)E, n_src, rows, W4, chunk);
+    BG_CUDA(cudaGetLastError());
+    return BG_OK;
+}

@@ -1,0 +1,58 @@
+"""Host-side index math with `jax.random` / `jax.lax` semantics.
+
+The action wrappers of the reference translate scores into (parent, parent)
+index pairs with `jax.lax.top_k`, `jax.random.choice(replace=False)`,
+`jnp.repeat(total_repeat_length=...)` and `jax.nn.softmax`
+(breedgym/vector/vec_wrappers.py:61-79,100-112, breedgym/wrappers.py:80-85).
+These are O(n) .. O(n^2) integer/float ops on a few hundred elements per env;
+they run on the host with NumPy, drawing random bits from the library's
+Threefry (`bg_random_bits`, `bg_key_split`) so the streams match jax's.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def shuffle_rounds(size: int) -> int:
+    return int(np.ceil(3 * np.log(max(1, size)) / np.log(np.iinfo(np.uint32).max)))
+
+
+def permutation(key: np.ndarray, n: int, layout: str = "legacy") -> np.ndarray:
+    """`jax.random.permutation(key, n)`: repeated stable sort by fresh 32-bit keys."""
+    x = np.arange(n, dtype=np.int64)
+    for _ in range(shuffle_rounds(n)):
+        ks = _lib.key_split(key, 2, layout)
+        key, sub = ks[0], ks[1]
+        x = x[np.argsort(_lib.random_bits(sub, n, layout), kind="stable")]
+    return x
+
+
+def choice_no_replace(key: np.ndarray, n_inputs: int, n_draws: int, layout: str = "legacy") -> np.ndarray:
+    if n_draws > n_inputs:
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    return permutation(key, n_inputs, layout)[:n_draws]
+
+
+def top_k(x: np.ndarray, k: int):
+    """`jax.lax.top_k` along the last axis: descending, ties -> lower index."""
+    x = np.asarray(x)
+    order = np.argsort(-x, axis=-1, kind="stable")[..., :k]
+    return np.take_along_axis(x, order, axis=-1), order
+
+
+def repeat_total(x: np.ndarray, repeats, total: int) -> np.ndarray:
+    """`jnp.repeat(x, repeats, axis=0, total_repeat_length=total)`: truncate or pad with the last row."""
+    x = np.asarray(x)
+    out = np.repeat(x, repeats, axis=0)
+    if len(out) >= total:
+        return out[:total]
+    return np.concatenate([out, np.repeat(x[-1:], total - len(out), axis=0)], axis=0)
+
+
+def softmax_f32(x: np.ndarray) -> np.ndarray:
+    """`jax.nn.softmax` in float32."""
+    x = np.asarray(x, dtype=np.float32)
+    e = np.exp(x - np.max(x, axis=-1, keepdims=True))
+    return e / np.sum(e, axis=-1, keepdims=True, dtype=np.float32)

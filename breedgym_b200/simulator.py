@@ -1,0 +1,341 @@
+"""`Simulator` -- drop-in for the `chromax.Simulator` surface BreedGym uses.
+
+The reference's operator API for the hot path is the Python object
+`chromax.Simulator`: constructed at
+breedgym/breedgym.py:36 and breedgym/vector/vec_env.py:45, then
+`.load_population`, `.set_seed`, `.cross`, `.GEBV`, `.GEBV_model`, `.corrcoef`,
+`.select`, `._diallel_indices`, `.double_haploid`.  This class keeps the same
+names, argument meaning and error behaviour, does the host-only work (map
+parsing, the Threefry key chain) and enqueues the sm_100a kernels of
+libbreedgym_b200 through the C ABI.  Per element, Python computes nothing.
+"""
+from __future__ import annotations
+
+import ctypes
+import random
+from pathlib import Path
+from typing import Callable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _lib
+from .population import PackedPopulation, ParentsView
+
+
+class TraitModel:
+    """chromax.trait_model.TraitModel: `dot(sum(pop, -1), effects) + offset`."""
+
+    def __init__(self, sim: "Simulator", marker_effects: np.ndarray, offset: float = 0.0):
+        self._sim = sim
+        self.marker_effects = np.ascontiguousarray(marker_effects, dtype=np.float32)
+        self.offset = offset
+        self.n_traits = self.marker_effects.shape[1]
+
+    def __call__(self, population) -> torch.Tensor:
+        """`float32[..., n_traits]` on the simulator's device."""
+        out = self._sim._gebv(self._sim.as_packed(population))
+        return out + self.offset if self.offset else out
+
+    @property
+    def positive_mask(self) -> np.ndarray:
+        return self.marker_effects > 0
+
+    @property
+    def max(self) -> np.ndarray:
+        return 2 * np.sum(self.marker_effects, axis=0, where=self.positive_mask) + self.offset
+
+    @property
+    def min(self) -> np.ndarray:
+        return 2 * np.sum(self.marker_effects, axis=0, where=~self.positive_mask) + self.offset
+
+    @property
+    def mean(self) -> np.ndarray:
+        return np.sum(self.marker_effects, axis=0) + self.offset
+
+    @property
+    def var(self) -> np.ndarray:
+        return np.sum(self.marker_effects**2, axis=0) / 2
+
+
+def _resolve_device(device) -> torch.device:
+    if device is None:
+        idx = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        return torch.device("cuda", idx)
+    if isinstance(device, (int, np.integer)):
+        return torch.device("cuda", int(device))
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError("breedgym_b200 runs on CUDA devices only (no CPU fallback)")
+    return torch.device("cuda", dev.index if dev.index is not None else 0)
+
+
+class Simulator:
+    """Breeding simulator bound to one B200."""
+
+    def __init__(
+        self,
+        genetic_map: Union[str, Path, pd.DataFrame],
+        trait_names: Optional[List[str]] = None,
+        chr_column: str = "CHR.PHYS",
+        position_column: str = "cM",
+        recombination_column: str = "RecombRate",
+        mutation: float = 0.0,
+        h2: Optional[np.ndarray] = None,
+        seed: Optional[int] = None,
+        device=None,
+        backend=None,
+        rng_layout: str = "legacy",
+        key_schedule: str = "S2",
+    ):
+        if rng_layout not in _lib.LAYOUT_ID:
+            raise ValueError(f"rng_layout must be one of {list(_lib.LAYOUT_ID)}")
+        if key_schedule not in _lib.SCHEDULE_ID:
+            raise ValueError(f"key_schedule must be one of {list(_lib.SCHEDULE_ID)}")
+        self.rng_layout = rng_layout
+        self.key_schedule = key_schedule
+        self.mutation = float(mutation)
+        self.device = _resolve_device(device)
+
+        if not isinstance(genetic_map, pd.DataFrame):
+            genetic_map = pd.read_table(genetic_map, sep="\t")
+        if trait_names is None:
+            skip = {"MRK.NAME", chr_column, position_column, recombination_column}
+            trait_names = [c for c in genetic_map.columns if c not in skip]
+        self.trait_names = list(trait_names)
+        self.n_markers = len(genetic_map)
+        chrom = genetic_map[chr_column].to_numpy()
+        first = np.ones(self.n_markers, dtype=bool)
+        first[1:] = chrom[1:] != chrom[:-1]
+        starts = np.flatnonzero(first)
+        self.chr_lens = np.diff(np.append(starts, self.n_markers))
+
+        if recombination_column in genetic_map.columns:
+            rec = np.array(genetic_map[recombination_column].to_numpy(), dtype=np.float64, copy=True)
+            rec[1:] = rec[:-1].copy()  # "recombine now" instead of "recombine after"
+        elif position_column in genetic_map.columns:
+            cm = np.asarray(genetic_map[position_column].to_numpy(), dtype=np.float64)
+            rec = np.zeros(self.n_markers, dtype=np.float64)
+            rec[1:] = 0.5 * (1.0 - np.exp(-2.0 * (cm[1:] - cm[:-1]) / 100.0))  # Haldane
+        else:
+            raise ValueError(f"genetic map needs a '{recombination_column}' or a '{position_column}' column")
+        rec[first] = 0.5
+        self.recombination_vec = rec.astype(np.float32)
+        if h2 is None:
+            h2 = np.full((len(self.trait_names),), 0.5)
+        self.h2 = np.asarray(h2)
+
+        effects = genetic_map[self.trait_names].to_numpy(dtype=np.float32)
+        self.GEBV_model = TraitModel(self, effects)
+
+        self._engine = ctypes.c_void_p()
+        lib = _lib.load()
+        _lib.check(lib.bg_engine_create(self.device.index, ctypes.byref(self._engine)))
+        eff = self.GEBV_model.marker_effects
+        _lib.check(lib.bg_engine_set_map(self._engine, _lib.nptr(self.recombination_vec), _lib.nptr(eff),
+                                         self.n_markers, eff.shape[1], self.mutation))
+        self.words_per_row = _lib.words_per_row(self.n_markers)
+
+        if seed is None:
+            seed = random.randint(0, 2**32)
+        self.random_key = _lib.key_data(seed)
+        # chromax draws the GxE effects at construction, consuming one split
+        self.random_key = self._split(self.random_key, 2)[0]
+
+    def __del__(self):
+        eng = getattr(self, "_engine", None)
+        if eng:
+            try:
+                _lib.load().bg_engine_destroy(eng)
+            except Exception:
+                pass
+            self._engine = None
+
+    # ---- helpers ---------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _split(self, key, num=2) -> np.ndarray:
+        return _lib.key_split(key, num, self.rng_layout)
+
+    def _next_key(self) -> np.ndarray:
+        ks = self._split(self.random_key, 2)
+        self.random_key = ks[0]
+        return ks[1]
+
+    def _layout(self) -> int:
+        return _lib.LAYOUT_ID[self.rng_layout]
+
+    def _schedule(self) -> int:
+        return _lib.SCHEDULE_ID[self.key_schedule]
+
+    def _empty_words(self, *lead) -> torch.Tensor:
+        return torch.empty((*lead, 2, self.words_per_row), dtype=torch.int32, device=self.device)
+
+    def _index_tensor(self, idx) -> torch.Tensor:
+        if isinstance(idx, torch.Tensor):
+            return idx.to(device=self.device, dtype=torch.int32).contiguous()
+        a = np.ascontiguousarray(np.asarray(idx), dtype=np.int32)
+        return torch.from_numpy(a).to(self.device)
+
+    def as_packed(self, population) -> PackedPopulation:
+        """Accept a PackedPopulation, or a bool array/tensor `[..., n, m, 2]` (packed on the device)."""
+        if isinstance(population, PackedPopulation):
+            if population.sim.words_per_row != self.words_per_row or population.words.device != self.device:
+                raise ValueError("population belongs to a different simulator / device")
+            return population
+        if isinstance(population, ParentsView):
+            population = np.asarray(population)
+        if isinstance(population, torch.Tensor):
+            b = population.to(device=self.device)
+        else:
+            b = torch.from_numpy(np.ascontiguousarray(np.asarray(population))).to(self.device)
+        if b.dim() < 3 or b.shape[-1] != 2 or b.shape[-2] != self.n_markers:
+            raise ValueError(f"population must have shape (..., n, {self.n_markers}, 2), got {tuple(b.shape)}")
+        b = (b != 0).contiguous()
+        lead = tuple(b.shape[:-2])
+        rows = int(np.prod(lead))
+        words = self._empty_words(*lead)
+        _lib.check(_lib.load().bg_pack(self._engine, b.data_ptr(), words.data_ptr(), rows, self._stream()))
+        return PackedPopulation(self, words)
+
+    def _gather(self, population: PackedPopulation, idx) -> PackedPopulation:
+        """`population[idx]` for a 1-D integer index (whole individuals)."""
+        it = self._index_tensor(idx).reshape(1, -1)
+        n = it.shape[1]
+        src = population.words.contiguous()
+        out = self._empty_words(n)
+        _lib.check(_lib.load().bg_gather_individuals(self._engine, src.data_ptr(), it.data_ptr(), out.data_ptr(),
+                                                     1, src.shape[0], n, 0, self._stream()))
+        return PackedPopulation(self, out)
+
+    def _gebv(self, population: PackedPopulation) -> torch.Tensor:
+        w = population.words.contiguous()
+        lead = tuple(w.shape[:-2])
+        rows = int(np.prod(lead))
+        T = self.GEBV_model.n_traits
+        out = torch.empty((*lead, T), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.load().bg_gebv(self._engine, w.data_ptr(), rows, out.data_ptr(), self._stream()))
+        return out
+
+    # ---- chromax.Simulator surface -----------------------------------------------
+    def set_seed(self, seed: int):
+        self.random_key = _lib.key_data(seed)
+
+    def load_population(self, file_name: Union[str, Path]) -> PackedPopulation:
+        file_name = Path(file_name)
+        if file_name.suffix == ".npy":
+            pop = np.load(file_name)
+        else:
+            pop = np.loadtxt(file_name, dtype="bool")
+            pop = pop.reshape(pop.shape[0], self.n_markers, 2)
+        return self.as_packed(pop)
+
+    def save_population(self, population, file_name: Union[str, Path]):
+        np.save(file_name, np.asarray(population), allow_pickle=False)
+
+    def cross(self, parents) -> PackedPopulation:
+        """Offspring of `parents[n, 2, m, 2]` (or of a lazy `population[action]` view)."""
+        k = self._next_key()
+        if isinstance(parents, ParentsView):
+            pop, pairs = parents.population, parents.pairs
+        else:
+            arr = parents if isinstance(parents, torch.Tensor) else np.asarray(parents)
+            if arr.ndim != 4 or arr.shape[1] != 2:
+                raise ValueError(f"parents must have shape (n, 2, m, 2), got {tuple(arr.shape)}")
+            n = arr.shape[0]
+            pop = self.as_packed(arr.reshape(2 * n, *arr.shape[2:]))
+            pairs = np.arange(2 * n, dtype=np.int32).reshape(n, 2)
+        return self._cross_indexed(pop, pairs, k)
+
+    def _cross_indexed(self, pop: PackedPopulation, pairs, k: np.ndarray) -> PackedPopulation:
+        src = pop.words.contiguous()
+        it = self._index_tensor(pairs)
+        if src.dim() == 3:  # one population
+            E, n_src, n = 1, src.shape[0], it.shape[0]
+            out = self._empty_words(n)
+        else:  # [E, n_src, 2, Wpad] with pairs [E, n, 2]
+            E, n_src, n = src.shape[0], src.shape[1], it.shape[1]
+            out = self._empty_words(E, n)
+        k = np.ascontiguousarray(k, dtype=np.uint32)
+        _lib.check(_lib.load().bg_cross(self._engine, src.data_ptr(), it.data_ptr(), out.data_ptr(), E, n_src, n,
+                                        _lib.nptr(k), self._layout(), self._schedule(), self._stream()))
+        return PackedPopulation(self, out)
+
+    def cross_envs(self, populations: PackedPopulation, actions) -> PackedPopulation:
+        """`vmap(cross)(populations[arange, actions])` with ONE key for all envs
+        (breedgym/vector/vec_env.py:75-77, 89-91)."""
+        return self._cross_indexed(populations, actions, self._next_key())
+
+    def double_haploid(self, population, n_offspring: int = 1) -> PackedPopulation:
+        pop = self.as_packed(population)
+        if pop.words.dim() != 3:
+            raise ValueError("double_haploid expects one population (n, m, 2)")
+        k = np.ascontiguousarray(self._next_key(), dtype=np.uint32)
+        n = len(pop)
+        out = self._empty_words(n, n_offspring)
+        _lib.check(_lib.load().bg_double_haploid(self._engine, pop.words.contiguous().data_ptr(), out.data_ptr(), n,
+                                                 n_offspring, _lib.nptr(k), self._layout(), self._schedule(),
+                                                 self._stream()))
+        if n_offspring == 1:
+            out = out[:, 0]
+        return PackedPopulation(self, out)
+
+    def GEBV(self, population) -> pd.DataFrame:
+        gebv = self.GEBV_model(population)
+        return pd.DataFrame(gebv.cpu().numpy(), columns=self.trait_names)
+
+    @property
+    def max_gebv(self):
+        return self.GEBV_model.max
+
+    @property
+    def min_gebv(self):
+        return self.GEBV_model.min
+
+    @property
+    def mean_gebv(self):
+        return self.GEBV_model.mean
+
+    def corrcoef(self, population) -> np.ndarray:
+        """Correlation of every individual's 2m alleles with the population mean."""
+        flat = self.as_packed(population).to_bool().reshape(len(population), -1).to(torch.float32)
+        stacked = torch.cat([flat.mean(dim=0, keepdim=True), flat], dim=0)
+        return torch.corrcoef(stacked)[0, 1:].cpu().numpy()
+
+    def select(self, population, k: int, f_index: Optional[Callable] = None) -> Tuple[PackedPopulation, np.ndarray]:
+        """Top-k individuals by `f_index` (default: GEBV summed over traits); ties -> lower index."""
+        pop = self.as_packed(population)
+        if pop.words.dim() != 3:
+            raise ValueError("select expects one population (n, m, 2)")
+        if k > len(pop):
+            raise ValueError(f"k={k} must not exceed the population size {len(pop)}")
+        if f_index is None:
+            values = self.GEBV_model(pop).sum(dim=-1)
+        else:
+            values = f_index(pop)
+        if isinstance(values, torch.Tensor):
+            values = values.detach().cpu().numpy()
+        values = np.asarray(values)
+        if values.ndim != 1:
+            raise ValueError("f_index must return one value per individual")
+        best = np.argsort(-values, kind="stable")[:k]
+        return self._gather(pop, best), best
+
+    @staticmethod
+    def _diallel_indices(indices: Sequence[int]) -> np.ndarray:
+        indices = np.asarray(indices)
+        a, b = np.triu_indices(len(indices), k=1)
+        return np.stack([indices[a], indices[b]], axis=1)
+
+    def diallel(self, population, n_offspring: int = 1) -> PackedPopulation:
+        pop = self.as_packed(population)
+        pairs = np.repeat(self._diallel_indices(np.arange(len(pop))), n_offspring, axis=0)
+        return self.cross(pop[pairs])
+
+    def random_crosses(self, population, n_crosses: int, n_offspring: int = 1):
+        pop = self.as_packed(population)
+        rng = np.random.default_rng(int(self._next_key()[1]))
+        pairs = rng.integers(0, len(pop), size=(n_crosses, 2))
+        return self.cross(pop[np.repeat(pairs, n_offspring, axis=0)]), pairs

@@ -1,0 +1,203 @@
+"""Vector environment (drop-in for `breedgym.vector.VecBreedGym`).
+
+Mirrors breedgym/vector/vec_env.py:30-134: `E` independent populations stepped
+together; ONE cross key per step shared by every env (the reference's
+`jax.vmap(simulator.cross, in_axes=(None, 0))` runs the key split once, so all
+envs see identical crossover masks -- reproduced on purpose); reward = max GEBV
+over (individuals, traits) at the end of an episode (or every step with
+`reward_shaping`); autoreset.
+
+State lives on the GPU as bit planes `int32[E, n, 2, Wpad]`.  A step is one
+C-ABI call (`bg_vec_step`): H2D of the actions, mask generation, blend, GEBV,
+reward reduction, D2H of GEBV / rewards.
+
+Multi-GPU (`env_shard=(begin, total)`): the E logical envs are partitioned into
+contiguous blocks, one process per GPU; every shard derives the same cross key
+and its own slice of the reset keys, so a sharded run is bit-identical to the
+single-GPU env -- no data-path collective, only the reward all-gather
+(`breedgym_b200.vector.sharded`).
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..gym_compat import VectorEnv, spaces
+from ..population import PackedPopulation
+from ..simulator import Simulator
+from ..utils.paths import DATA_PATH
+
+GENOME_FILE = DATA_PATH.joinpath("small_geno.npy")
+
+
+class VecBreedGym(VectorEnv):
+    def __init__(
+        self,
+        num_envs: int = 1,
+        initial_population: Union[str, Path, np.ndarray, PackedPopulation] = GENOME_FILE,
+        individual_per_gen: Optional[int] = None,
+        num_generations: int = 10,
+        autoreset: bool = True,
+        reward_shaping: bool = False,
+        info_device: str = "host",
+        env_shard: Optional[Tuple[int, int]] = None,
+        **kwargs,
+    ):
+        self.num_envs = num_envs
+        self.num_generations = num_generations
+        self.autoreset = autoreset
+        self.reward_shaping = reward_shaping
+        if info_device not in ("host", "device"):
+            raise ValueError("info_device must be 'host' or 'device'")
+        self.info_device = info_device
+        self.simulator = Simulator(**kwargs)
+        self.device = self.simulator.device
+        # logical env range of this shard: envs [begin, begin + num_envs) of `total`
+        self.env_shard = (0, num_envs) if env_shard is None else (int(env_shard[0]), int(env_shard[1]))
+        if self.env_shard[0] < 0 or self.env_shard[0] + num_envs > self.env_shard[1]:
+            raise ValueError("env_shard=(begin, total) must contain [begin, begin + num_envs)")
+
+        if isinstance(initial_population, (str, Path)):
+            germplasm = self.simulator.load_population(initial_population)
+        else:
+            germplasm = self.simulator.as_packed(initial_population)
+        self.germplasm = germplasm
+        if individual_per_gen is None:
+            individual_per_gen = len(self.germplasm)
+        self.individual_per_gen = individual_per_gen
+        self._set_spaces()
+
+        self.populations = None
+        self.step_idx = None
+        self.reset_infos = {}
+        self.random_key = None
+        self._pinned = {}
+        self._h2d_done = None
+
+    def _set_spaces(self):
+        n, m = self.individual_per_gen, self.germplasm.shape[1]
+        self.single_observation_space = spaces.Box(low=0, high=1, shape=(n, m, 2), dtype=np.int8)
+        self.single_action_space = spaces.Box(low=0, high=n, shape=(n, 2), dtype=np.int32)
+        self.observation_space = spaces.Box(low=0, high=1, shape=(self.num_envs, n, m, 2), dtype=np.int8)
+        self.action_space = spaces.Box(low=0, high=n, shape=(self.num_envs, n, 2), dtype=np.int32)
+
+    # ---- buffers -------------------------------------------------------------------
+    def _pinned_buf(self, name: str, shape, dtype) -> torch.Tensor:
+        buf = self._pinned.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+            self._pinned[name] = buf
+        return buf
+
+    # ---- the hot path ----------------------------------------------------------------
+    def cross(self, parents_idx) -> PackedPopulation:
+        """Offspring of `populations[arange, parents_idx]`, one key for all envs (vec_env.py:75-77)."""
+        return self.simulator.cross_envs(self.populations, parents_idx)
+
+    def step(self, actions):
+        sim, E, T = self.simulator, self.num_envs, self.simulator.GEBV_model.n_traits
+        done = self.step_idx + 1 == self.num_generations
+        need_reward = self.reward_shaping or done
+        host_info = self.info_device == "host"
+
+        src = self.populations.words
+        n_src = src.shape[1]
+        if isinstance(actions, torch.Tensor) and actions.is_cuda:
+            act_dev = actions.to(device=self.device, dtype=torch.int32).contiguous()
+            act_host_ptr = None
+        else:
+            a = np.asarray(actions)
+            act_pin = self._pinned_buf("actions", a.shape, torch.int32)
+            if self._h2d_done is not None:  # previous async H2D must have left the staging buffer
+                self._h2d_done.synchronize()
+            act_pin.numpy()[...] = a  # int64 -> int32 conversion happens in this copy
+            act_dev = torch.empty(a.shape, dtype=torch.int32, device=self.device)
+            act_host_ptr = act_pin.data_ptr()
+        if act_dev.dim() != 3 or act_dev.shape[0] != E or act_dev.shape[2] != 2:
+            raise ValueError(f"actions must have shape ({E}, n, 2), got {tuple(act_dev.shape)}")
+        n = act_dev.shape[1]
+
+        out = sim._empty_words(E, n)
+        gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
+        rew_dev = torch.empty((E,), dtype=torch.float32, device=self.device) if need_reward else None
+        gebv_pin = self._pinned_buf("gebv", (E, n, T), torch.float32) if host_info else None
+        rew_pin = self._pinned_buf("rews", (E,), torch.float32) if need_reward else None
+
+        k = np.ascontiguousarray(sim._next_key(), dtype=np.uint32)
+        _lib.check(_lib.load().bg_vec_step(
+            sim._engine, src.data_ptr(), out.data_ptr(), act_host_ptr, act_dev.data_ptr(), E, n_src, n,
+            _lib.nptr(k), sim._layout(), sim._schedule(), gebv_dev.data_ptr(),
+            rew_dev.data_ptr() if need_reward else None,
+            gebv_pin.data_ptr() if host_info else None,
+            rew_pin.data_ptr() if need_reward else None,
+            sim._stream()))
+        if act_host_ptr is not None and not (host_info or need_reward):  # no sync happened inside the call
+            self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record(torch.cuda.current_stream(self.device))
+        else:
+            self._h2d_done = None
+        self.populations = PackedPopulation(sim, out)
+        self.step_idx += 1
+
+        infos = {"GEBV": gebv_pin.numpy().copy() if host_info else gebv_dev}
+        rews = rew_pin.numpy().copy() if need_reward else np.zeros(E)
+
+        if done and self.autoreset:
+            self.reset()
+
+        terminated = np.full(E, False)
+        truncated = np.full(E, done)
+        return self.populations, rews, terminated, truncated, infos
+
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        self.step_idx = 0
+        if seed is not None:
+            self.simulator.set_seed(seed)
+            self.random_key = _lib.key_data(seed)
+        elif self.random_key is None:
+            seed = np.random.randint(2**32)
+            self.random_key = _lib.key_data(seed)
+
+        if options is not None and "individual_per_gen" in options.keys():
+            self.individual_per_gen = options["individual_per_gen"]
+            self._set_spaces()
+
+        begin, total = self.env_shard
+        sim, E, n = self.simulator, self.num_envs, self.individual_per_gen
+        key = np.ascontiguousarray(self.random_key, dtype=np.uint32)
+        idx = torch.empty((E, n), dtype=torch.int32, device=self.device)
+        lib = _lib.load()
+        # env g draws permutation(keys[1 + g], N)[:n] with keys = split(random_key, total + 1)
+        _lib.check(lib.bg_reset_indices(sim._engine, _lib.nptr(key), total, begin, E, len(self.germplasm), n,
+                                        sim._layout(), idx.data_ptr(), sim._stream()))
+        self.random_key = sim._split(self.random_key, total + 1)[0]
+        words = sim._empty_words(E, n)
+        germ = self.germplasm.words.contiguous()
+        _lib.check(lib.bg_gather_individuals(sim._engine, germ.data_ptr(), idx.data_ptr(), words.data_ptr(), E,
+                                             germ.shape[0], n, 0, sim._stream()))
+        self._reset_indices = idx
+        self.populations = PackedPopulation(sim, words)
+        self.reset_infos = self.get_info()
+        return self.populations, self.reset_infos
+
+    def get_info(self) -> dict:
+        gebv = self.simulator.GEBV_model(self.populations)
+        return {"GEBV": gebv.cpu().numpy() if self.info_device == "host" else gebv}
+
+    def set_attr(self, name, values):
+        return setattr(self, name, values)
+
+
+class _VecBreedGym(VecBreedGym):
+    """Shard worker of the reference's DistributedBreedGym (vec_env.py:140-147): scalar ter/tru."""
+
+    def step(self, action):
+        obs, rews, ter, tru, infos = super().step(action)
+        assert np.all(ter == ter[0])
+        assert np.all(tru == tru[0])
+        return obs, rews, ter[0], tru[0], infos

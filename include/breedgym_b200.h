@@ -1,0 +1,156 @@
+/* breedgym_b200 -- C ABI of the B200-native breeding-simulation engine.
+ *
+ * Drop-in boundary for the ONE hot path of younik/breedgym: meiosis/cross ->
+ * GEBV scoring -> vector-env step.  The reference has no FFI layer: its operator
+ * API is the Python object `chromax.Simulator` as BreedGym calls it.  Each entry
+ * point below names the reference interface it replaces (paths relative to
+ * /root/reference; "chromax:" = the un-vendored PyPI dependency).
+ * The ctypes binding a maintainer would add is shown in INTEGRATION.md and is
+ * what breedgym_b200/_lib.py does.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative BG_E* code on failure;
+ *     bg_last_error() gives the message (thread local).  No C++ exception crosses.
+ *   - all population / action / output buffers are CALLER-allocated device memory
+ *     (e.g. torch CUDA tensors' data_ptr()); the library never frees or retains
+ *     them.  The engine owns only its copies of the map constants and scratch.
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as
+ *     void*); nothing synchronises unless stated.  One engine per (device,thread).
+ *   - packed population layout: uint32 words [rows][2][Wpad], haplotype-major bit
+ *     planes, marker j <-> bit (j & 31) of word (j >> 5), Wpad = bg_words_per_row(m)
+ *     (ceil(m/32) rounded up to a multiple of 4 => rows are 16-byte aligned);
+ *     padding bits are zero.  The reference's byte layout `bool[rows][m][2]`
+ *     (breedgym/breedgym.py:47, vec_env.py:57-62) appears only at bg_pack/bg_unpack.
+ */
+#ifndef BREEDGYM_B200_H
+#define BREEDGYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BG_VERSION 100
+
+#define BG_OK 0
+#define BG_EINVAL (-1)   /* bad argument */
+#define BG_ECUDA (-2)    /* CUDA runtime error */
+#define BG_ENOMEM (-3)   /* allocation failure */
+#define BG_ELIMIT (-4)   /* shape beyond a documented kernel limit */
+#define BG_ESTATE (-5)   /* engine not configured (bg_engine_set_map missing) */
+
+/* jax PRNG bit layout */
+#define BG_LAYOUT_LEGACY 0        /* jax_threefry_partitionable=False (jax < 0.5) */
+#define BG_LAYOUT_PARTITIONABLE 1 /* jax_threefry_partitionable=True  (jax >= 0.5) */
+/* chromax per-gamete key schedule */
+#define BG_SCHEDULE_S1 1 /* gamete key drives the recombination draw directly */
+#define BG_SCHEDULE_S2 2 /* gamete key is split into (recombination, mutation) keys */
+
+typedef struct bg_engine bg_engine;
+
+int bg_version(void);
+const char *bg_last_error(void);
+
+/* ---- host-side PRNG helpers (no GPU touched) ------------------------------
+ * Replace jax.random.key/split/bits as used for the KEY CHAIN only
+ * (chromax: Simulator.cross `random_key, k = split(random_key)`;
+ *  breedgym/vector/vec_env.py:115,120; breedgym/vector/vec_wrappers.py:82). */
+void bg_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t out[2]);
+int bg_key_split(const uint32_t key[2], int64_t num, int layout, uint32_t *out /* [num][2] */);
+int bg_random_bits(const uint32_t key[2], int64_t n, int layout, uint32_t *out /* [n] */);
+/* integer form of `uniform(key) < r`: (bits >> 9) < T,  T = clamp(ceil(r * 2^23), 0, 2^23) */
+int bg_thresholds(const float *r, int64_t m, uint32_t *out /* [m] */);
+
+/* ---- engine ---------------------------------------------------------------- */
+int64_t bg_words_per_row(int64_t n_markers);
+
+/* chromax: Simulator.__init__ (device placement of recombination_vec and
+ * GEBV_model.marker_effects; breedgym/breedgym.py:36, vec_env.py:45). */
+int bg_engine_create(int device, bg_engine **out);
+int bg_engine_destroy(bg_engine *eng);
+/* recomb: host float32[m] (already shifted / chromosome starts = 0.5);
+ * effects: host float32[m][n_traits] row-major; mutation: chromax `mutation`. */
+int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects, int64_t n_markers,
+                      int32_t n_traits, float mutation);
+
+/* ---- layout conversion ------------------------------------------------------
+ * chromax: Simulator.load_population -> device array (breedgym/breedgym.py:38-42);
+ * bg_unpack materialises the observation `bool[rows][m][2]` on request. */
+int bg_pack(bg_engine *eng, const uint8_t *bool_in, uint32_t *packed_out, int64_t rows, void *stream);
+int bg_unpack(bg_engine *eng, const uint32_t *packed_in, uint8_t *bool_out, int64_t rows, void *stream);
+/* dst[e][r] = src[e * src_env_rows + idx[e][r]]  (whole individuals, both planes).
+ * `populations[arange, idx]` style gathers: germplasm[selected] (breedgym.py:125,
+ * vec_env.py:126-128 after the permutation), Simulator.select's pop[idx].
+ * src_env_rows = 0 broadcasts one source population to every env. */
+int bg_gather_individuals(bg_engine *eng, const uint32_t *src, const int32_t *idx /* dev [E][n] */, uint32_t *dst,
+                          int64_t E, int64_t n_src, int64_t n, int64_t src_env_rows, void *stream);
+
+/* ---- meiosis / cross --------------------------------------------------------
+ * Replaces `parents = population[action]; simulator.cross(parents)`
+ * (breedgym/breedgym.py:142-143) and the vmapped, SHARED-KEY version
+ * (breedgym/vector/vec_env.py:75-77,89-91) -- chromax: functional.cross/_meiosis.
+ * pop:     packed [E][n_src][2][Wpad]
+ * parents: device int32 [E][n][2], jnp indexing semantics (negatives wrap once,
+ *          then clamp)
+ * out:     packed [E][n][2][Wpad]; out[e][i][p] = gamete of pop[e][parents[e][i][p]]
+ * cross_key: the `k` of `random_key, k = split(random_key)`; gamete (i,p) uses key
+ *          #(2i+p) of split(k, 2n) for EVERY env (the reference's vmap shares it).
+ * E == 1 runs the fused unique-key kernel; E > 1 generates the 2n masks once and
+ * blends all envs against them. */
+int bg_cross(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src,
+             int64_t n, const uint32_t cross_key[2], int layout, int schedule, void *stream);
+
+/* chromax: Simulator.double_haploid / functional.double_haploid
+ * (breedgym/vector/breeding_programs_env.py:41).  pop packed [n][2][Wpad] ->
+ * out packed [n][n_offspring][2][Wpad], both planes = the gamete of key
+ * #(i*n_offspring+o) of split(k, n*n_offspring). */
+int bg_double_haploid(bg_engine *eng, const uint32_t *pop, uint32_t *out, int64_t n, int64_t n_offspring,
+                      const uint32_t cross_key[2], int layout, int schedule, void *stream);
+
+/* crossover masks only (tests / diagnostics): mask_out [rows][Wpad], inclusive
+ * prefix-XOR of the recombination draws of key #q of split(k, rows). */
+int bg_meiosis_masks(bg_engine *eng, uint32_t *mask_out, int64_t rows, const uint32_t cross_key[2], int layout,
+                     int schedule, void *stream);
+
+/* ---- GEBV -------------------------------------------------------------------
+ * chromax: TraitModel.__call__ = dot(sum(pop,-1), effects) (+0 offset) as called
+ * from Simulator.GEBV / GEBV_model (breedgym/breedgym.py:233, vec_env.py:132-134).
+ * pop packed [rows][2][Wpad] -> out float32 [rows][n_traits].
+ * Arithmetic: exact 64-bit fixed point of the float32 effects, one final rounding
+ * to float32 (deterministic; differs from a float64 dot by < 1 ulp of float32). */
+int bg_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, void *stream);
+/* same result through the straightforward bit-test kernel (cross-check / fallback
+ * shapes); algorithm id for bg_gebv: 0 auto, 1 direct, 2 byte-LUT */
+int bg_gebv_algo(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, int algo, void *stream);
+
+/* rews = np.max(infos["GEBV"], axis=(1,2))  (breedgym/vector/vec_env.py:97):
+ * gebv float32 [E][per_env] -> out float32 [E] */
+int bg_reduce_max(bg_engine *eng, const float *gebv, int64_t E, int64_t per_env, float *out, void *stream);
+/* np.mean(GEBV.to_numpy()) (breedgym/breedgym.py:153), accumulated in float64 */
+int bg_reduce_mean(bg_engine *eng, const float *gebv, int64_t E, int64_t per_env, float *out, void *stream);
+
+/* ---- reset ------------------------------------------------------------------
+ * VecBreedGym.reset's `_random_selection` (breedgym/vector/vec_env.py:22-27,
+ * 120-128): env e draws permutation(keys[1+e], n_germ)[:n] where
+ * keys = split(random_key, E_total+1).  A shard computes envs
+ * [env_begin, env_begin+E) of the E_total logical envs; idx_out device int32 [E][n]
+ * (then bg_gather_individuals(germplasm, idx_out, ..., src_env_rows = 0)). */
+int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_total, int64_t env_begin, int64_t E,
+                     int64_t n_germ, int64_t n, int layout, int32_t *idx_out, void *stream);
+
+/* ---- one-call vector-env step ------------------------------------------------
+ * VecBreedGym.step hot path (breedgym/vector/vec_env.py:88-100) with host
+ * buffers at the boundary: copies actions_host (int32 [E][n][2], pinned or
+ * pageable) to `actions_dev`, runs cross -> GEBV (-> max reward), copies
+ * gebv/reward back to the host buffers when non-NULL, and synchronises the stream
+ * iff any device->host copy was requested. */
+int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_t *actions_host, int32_t *actions_dev,
+                int64_t E, int64_t n_src, int64_t n, const uint32_t cross_key[2], int layout, int schedule,
+                float *gebv_dev /* [E][n][T] */, float *reward_dev /* [E] or NULL */, float *gebv_host /* or NULL */,
+                float *reward_host /* or NULL */, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BREEDGYM_B200_H */

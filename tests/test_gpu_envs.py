@@ -1,0 +1,344 @@
+"""Environment-level tests on the GPU: the reference's own test-suite scenarios
+(tests/test_env.py, tests/test_vec.py, tests/test_wrappers.py of younik/breedgym) re-run against
+this implementation, with the un-evaluable golden rewards replaced by whole-trajectory parity
+against the CPU oracle (same seeds, same actions)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import chromax_ref as cr
+from oracle import jax_prng as jp
+
+pytestmark = pytest.mark.gpu
+
+DATA = Path(__file__).resolve().parents[1] / "breedgym_b200" / "data"
+GENOME = DATA / "sample_geno.npy"  # (200, 1000, 2)
+GMAP = DATA / "sample_with_r_genetic_map.txt"  # 1000 markers, trait Yield
+RTOL = 1e-5
+
+
+def gym():
+    from breedgym_b200 import gym_compat
+
+    return gym_compat
+
+
+def oracle_sim(sim, seed):
+    return cr.OracleSimulator(sim.recombination_vec, sim.GEBV_model.marker_effects, seed=seed,
+                              mutation=sim.mutation, schedule=sim.key_schedule, layout=sim.rng_layout)
+
+
+# ---- tests/test_env.py ------------------------------------------------------------------
+def test_reset_population(cuda_device):
+    env = gym().make("breedgym:BreedGym", initial_population=GENOME, genetic_map=GMAP)
+    pop, _ = env.reset()
+    init_pop = np.copy(pop)
+    env.step(np.asarray(env.action_space.sample()) % len(pop))
+    pop, _ = env.reset()
+    assert np.all(init_pop == pop)
+    assert np.array_equal(init_pop, np.load(GENOME))
+
+
+@pytest.mark.parametrize("n", [1, 5, 10])
+def test_num_progenies(cuda_device, n):
+    env = gym().make("breedgym:BreedGym", initial_population=GENOME, genetic_map=GMAP)
+    pop, _ = env.reset()
+    action = np.random.randint(len(pop), size=(n, 2))
+    obs, _, _, _, info = env.step(action)
+    assert len(env.population) == n and obs.shape == (n, 1000, 2)
+    assert env.observation_space.shape == (n, 1000, 2)
+    assert info["GEBV"].shape == (n, 1)
+
+
+def test_caching(cuda_device):
+    env = gym().make("breedgym:BreedGym", initial_population=GENOME, genetic_map=GMAP)
+    env.reset()
+    GEBV = env.unwrapped.GEBV
+    GEBV_copy = np.copy(GEBV)
+    GEBV2 = env.unwrapped.GEBV
+    assert id(GEBV) == id(GEBV2)
+    assert np.all(GEBV_copy == GEBV2)
+    corrcoef = env.corrcoef
+    corrcoef_copy = np.copy(corrcoef)
+    corrcoef2 = env.corrcoef
+    assert id(corrcoef) == id(corrcoef2)
+    assert np.all(corrcoef_copy == corrcoef2)
+    env.step(np.array([[1, 3], [4, 2]]))
+    assert id(corrcoef) != id(env.corrcoef)
+    assert id(GEBV) != id(env.unwrapped.GEBV)
+
+
+def test_reward_shaping(cuda_device):
+    env = gym().make("breedgym:BreedGym", initial_population=GENOME, genetic_map=GMAP, reward_shaping=False)
+    pop, _ = env.reset()
+    for _ in range(9):
+        action = np.asarray(env.action_space.sample()) % len(pop)
+        pop, reward, _, truncated, _ = env.step(action)
+        assert reward == 0
+        assert not truncated
+    action = np.asarray(env.action_space.sample()) % len(pop)
+    _, reward, _, truncated, _ = env.step(action)
+    assert reward != 0
+    assert truncated
+    env2 = gym().make("breedgym:BreedGym", initial_population=GENOME, genetic_map=GMAP, reward_shaping=True)
+    pop, _ = env2.reset()
+    action = np.asarray(env2.action_space.sample()) % len(pop)
+    _, reward, _, _, _ = env2.step(action)
+    assert reward != 0
+
+
+@pytest.mark.parametrize("layout", ["legacy", "partitionable"])
+def test_deterministic_trajectory_matches_oracle(cuda_device, layout):
+    """Reference tests/test_env.py:103-119 (seed 7, fixed 10-pair action x 10 generations); the golden
+    reward there needs chromax.sample_data, so the whole trajectory is checked against the oracle."""
+    env = gym().make("breedgym:BreedGym", initial_population=GENOME, genetic_map=GMAP, reward_shaping=False,
+                     rng_layout=layout)
+    env.reset(seed=7)
+    osim = oracle_sim(env.simulator, 7)
+    opop = np.load(GENOME)
+    action = np.array([[1, 2], [1, 5], [1, 7], [2, 5], [2, 9], [4, 7], [4, 8], [5, 9], [6, 8], [6, 9]])
+    for _ in range(10):
+        obs, r, _, tru, info = env.step(action)
+        opop = osim.cross(opop[action])
+        assert np.array_equal(np.asarray(obs), opop)
+        assert np.allclose(info["GEBV"].to_numpy(), cr.gebv(opop, osim.effects), rtol=RTOL, atol=0)
+    assert tru
+    assert abs(r - np.mean(cr.gebv(opop, osim.effects))) <= RTOL * abs(r)
+    # same seed -> same trajectory
+    env.reset(seed=7)
+    for _ in range(10):
+        obs2, r2, _, _, _ = env.step(action)
+    assert r2 == r and np.array_equal(np.asarray(obs2), opop)
+
+
+def test_reset_subset_uses_np_random(cuda_device):
+    env = gym().make("breedgym:BreedGym", initial_population=GENOME, genetic_map=GMAP)
+    pop, _ = env.reset(seed=3, options={"n_individuals": 17})
+    sel = np.random.Generator(np.random.PCG64(np.random.SeedSequence(3))).choice(200, 17, replace=False)
+    assert np.array_equal(np.asarray(pop), np.load(GENOME)[sel])
+
+
+# ---- tests/test_vec.py --------------------------------------------------------------------
+def test_vec(cuda_device):
+    num_envs, n = 8, 200
+    env = gym().make("VecBreedGym", num_envs=num_envs, initial_population=GENOME, genetic_map=GMAP,
+                     individual_per_gen=n)
+    pop, _ = env.reset()
+    expected_shape = (num_envs, n, env.simulator.n_markers, 2)
+    assert pop.shape == expected_shape
+    actions = np.random.randint(0, n, size=(num_envs, n, 2))
+    new_pop, reward, terminated, truncated, infos = env.step(actions)
+    assert new_pop.shape == expected_shape
+    assert reward.shape == (num_envs,)
+    assert np.all(~terminated)
+    assert np.all(~truncated)
+    assert isinstance(infos, dict)
+    assert len(infos["GEBV"]) == num_envs
+    for info in infos["GEBV"]:
+        assert info.shape == (n, 1)
+
+
+def test_vec_multi_trait_info_shape(cuda_device):
+    env = gym().make("VecBreedGym", num_envs=2, initial_population=np.random.rand(30, 9839, 2) < 0.5,
+                     genetic_map=DATA / "wheat_genetic_map.csv", individual_per_gen=20)
+    _, infos = env.reset(seed=0)
+    assert infos["GEBV"].shape == (2, 20, 7)
+    assert len(env.simulator.chr_lens) == 21
+
+
+@pytest.mark.parametrize("layout", ["legacy", "partitionable"])
+def test_vec_deterministic_trajectory_matches_oracle(cuda_device, layout):
+    """Reference tests/test_vec.py:115-133: E=4, n=200, seed 7, 20 random steps (spans an autoreset)."""
+    num_envs, n = 4, 200
+    env = gym().make("VecBreedGym", num_envs=num_envs, initial_population=GENOME, genetic_map=GMAP,
+                     individual_per_gen=n, rng_layout=layout)
+    germ = np.load(GENOME)
+    np.random.seed(seed=7)
+    pop, infos = env.reset(seed=7)
+    osim = oracle_sim(env.simulator, 7)
+    okey, opops, _ = cr.vec_reset(germ, n, num_envs, jp.key(7), layout)
+    assert np.array_equal(np.asarray(pop), opops)
+    assert np.allclose(infos["GEBV"], cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)
+    for step in range(20):
+        action = np.random.randint(len(pop), size=(num_envs, n, 2))  # len(pop) == num_envs, as in the reference
+        pop, rews, ter, tru, infos = env.step(action)
+        opops = cr.vec_step(osim, opops, action)
+        g = cr.gebv(opops, osim.effects)
+        assert np.allclose(infos["GEBV"], g, rtol=RTOL, atol=0)
+        if step % 10 == 9:
+            assert np.all(tru)
+            assert np.allclose(rews, g.max(axis=(1, 2)), rtol=RTOL, atol=0)
+            okey, opops, _ = cr.vec_reset(germ, n, num_envs, okey, layout)  # autoreset
+        else:
+            assert not np.any(tru) and np.all(rews == 0)
+        assert np.array_equal(np.asarray(pop), opops)
+    assert np.array_equal(env.random_key, okey)
+
+
+def test_selection_vec_and_gebv_policy_matches_oracle(cuda_device):
+    """Reference tests/test_vec.py:43-69,136-154 with the oracle replaying the wrapper's index math."""
+    num_envs, n = 4, 200
+    env = gym().make("SelectionScores", k=10, num_envs=num_envs, initial_population=GENOME, genetic_map=GMAP,
+                     individual_per_gen=n, trait_names=["Yield"])
+    pop, infos = env.reset(seed=7)
+    assert pop.shape == (num_envs, n, 1000, 2)
+    germ = np.load(GENOME)
+    osim = oracle_sim(env.simulator, 7)
+    okey, opops, _ = cr.vec_reset(germ, n, num_envs, jp.key(7), "legacy")
+    for _ in range(10):
+        scores = infos["GEBV"].squeeze()
+        _, rews, _, tru, infos = env.step(scores)
+        keys = jp.split(okey, num_envs + 1)
+        okey = keys[0]
+        acts = []
+        for e in range(num_envs):
+            _, best = jp.top_k(cr.gebv(opops[e], osim.effects)[:, 0].astype(np.float32), 10)
+            d = cr.diallel_indices(best)
+            sel = jp.choice_no_replace(keys[1 + e], len(d), 45)
+            acts.append(jp.repeat_total(d[sel], int(np.ceil(n / 45)), n))
+        opops = cr.vec_step(osim, opops, np.stack(acts))
+        for info in infos["GEBV"]:
+            assert info.shape == (n, 1)
+    assert np.all(tru)
+    assert np.allclose(rews, cr.gebv(opops, osim.effects).max(axis=(1, 2)), rtol=RTOL, atol=0)
+    assert rews.min() > cr.gebv(germ, osim.effects).mean()  # selection improves the population
+
+
+def test_vec_wrapper_n_crosses(cuda_device):
+    from breedgym_b200.vector import SelectionScores, VecBreedGym
+
+    env = VecBreedGym(num_envs=4, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=200,
+                      trait_names=["Yield"])
+    wrap_env = SelectionScores(env, k=10, n_crosses=20)
+    _, infos = wrap_env.reset(seed=7)
+    pop, _, _, _, _ = wrap_env.step(infos["GEBV"].squeeze())
+    assert pop.shape[1] == 200
+    for k, nc in ((100, 201), (2, 10), (1, 1), (500, 10)):
+        with pytest.raises(ValueError):
+            SelectionScores(env, k=k, n_crosses=nc)
+
+
+def test_vec_pair_score_and_ravel_index(cuda_device):
+    from breedgym_b200.vector import PairScores, RavelIndex, VecBreedGym
+
+    num_envs, n = 3, 60
+    env = gym().make("PairScores", num_envs=num_envs, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n)
+    _, infos = env.reset(seed=7)
+    for _ in range(10):
+        gebvs = infos["GEBV"].squeeze()
+        scores = np.stack([np.add.outer(g, g) for g in gebvs])
+        _, rews, _, tru, infos = env.step(scores)
+        assert infos["low_level_actions"].shape == (num_envs, n, 2)
+    assert np.all(tru) and rews.shape == (num_envs,) and np.all(rews != 0)
+
+    base = PairScores(VecBreedGym(num_envs=2, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n))
+    rav = RavelIndex(base)
+    rav.reset(seed=1)
+    flat = np.random.randint(0, n * n, size=(2, n))
+    pop, _, _, _, _ = rav.step(flat)
+    assert pop.shape == (2, n, 1000, 2)
+    assert np.array_equal(rav._convert_actions(flat), np.stack([flat // n, flat % n], axis=-1))
+
+
+def test_sharded_reset_and_step_equal_the_unsharded_env(cuda_device):
+    """Multi-GPU contract checked on one GPU: two shards [0,3) and [3,5) of a 5-env run reproduce the
+    5-env VecBreedGym exactly (replicated constants, shared cross key, sliced reset keys)."""
+    from breedgym_b200.vector import VecBreedGym
+
+    n = 50
+    kw = dict(initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n)
+    full = VecBreedGym(num_envs=5, **kw)
+    a = VecBreedGym(num_envs=3, env_shard=(0, 5), **kw)
+    b = VecBreedGym(num_envs=2, env_shard=(3, 5), **kw)
+    pf, _ = full.reset(seed=11)
+    pa, _ = a.reset(seed=11)
+    pb, _ = b.reset(seed=11)
+    assert np.array_equal(np.asarray(pf), np.concatenate([np.asarray(pa), np.asarray(pb)]))
+    rng = np.random.default_rng(0)
+    for _ in range(12):  # crosses an autoreset
+        act = rng.integers(0, n, (5, n, 2))
+        pf, rf, _, _, _ = full.step(act)
+        pa, ra, _, _, _ = a.step(act[:3])
+        pb, rb, _, _, _ = b.step(act[3:])
+        assert np.array_equal(np.asarray(pf), np.concatenate([np.asarray(pa), np.asarray(pb)]))
+        assert np.array_equal(rf, np.concatenate([ra, rb]))
+    assert np.array_equal(full.random_key, a.random_key) and np.array_equal(full.random_key, b.random_key)
+
+
+# ---- tests/test_wrappers.py -----------------------------------------------------------------
+def _check_obs(obs, n):
+    assert len(obs["GEBV"]) == n and len(obs["corrcoef"]) == n
+    assert np.all(obs["corrcoef"] >= -1) and np.all(obs["corrcoef"] <= 1)
+
+
+def test_simplified_env(cuda_device):
+    n = 200
+    env = gym().make("breedgym:SimplifiedBreedGym", individual_per_gen=n, initial_population=GENOME, genetic_map=GMAP)
+    obs, _ = env.reset()
+    _check_obs(obs, n)
+    for action in ({"n_bests": 10, "n_crosses": 20}, {"n_bests": 21, "n_crosses": 200}, {"n_bests": 2, "n_crosses": 1}):
+        obs, _, _, _, _ = env.step(action)
+        _check_obs(obs, n)
+    for bad in ({"n_bests": 100, "n_crosses": 201}, {"n_bests": 2, "n_crosses": 10}, {"n_bests": 1, "n_crosses": 1},
+                {"n_bests": 500, "n_crosses": 10}):
+        with pytest.raises(Exception):
+            env.step(bad)
+
+
+def test_kbest_env_and_policy_matches_oracle(cuda_device):
+    n = 200
+    env = gym().make("breedgym:KBestBreedGym", individual_per_gen=n, initial_population=GENOME, genetic_map=GMAP,
+                     trait_names=["Yield"])
+    obs, _ = env.reset(seed=7)
+    _check_obs(obs, n)
+    germ = np.load(GENOME)
+    osim = oracle_sim(env.simulator, 7)
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(7)))
+    opop = germ[rng.choice(200, n, replace=False)]
+    assert np.array_equal(np.asarray(env.population), opop)
+    for _ in range(10):
+        obs, r, _, tru, _ = env.step(10)
+        _check_obs(obs, n)
+        _, best = jp.top_k(cr.gebv(opop, osim.effects)[:, 0].astype(np.float32), 10)
+        sel = opop[best]
+        pairs = cr.diallel_indices(np.arange(10))
+        chosen = rng.choice(len(pairs), 45, replace=False)
+        act = np.repeat(pairs[chosen], int(np.ceil(n / 45)), axis=0)[:n]
+        opop = osim.cross(sel[act])
+        assert np.array_equal(np.asarray(env.population), opop)
+        assert np.allclose(obs["corrcoef"], cr.simplified_correlation(opop), rtol=1e-4, atol=1e-5)
+    assert tru and abs(r - cr.gebv(opop, osim.effects).mean()) <= RTOL * abs(r)
+    for bad in (1, 21):
+        with pytest.raises(Exception):
+            env.step(bad)
+
+
+def test_corrcoef_and_select_match_oracle(cuda_device):
+    from breedgym_b200.simulator import Simulator
+
+    sim = Simulator(genetic_map=GMAP, device=0, seed=0)
+    germ = np.load(GENOME)
+    pop = sim.as_packed(germ)
+    assert np.allclose(sim.corrcoef(pop), cr.corrcoef(germ), rtol=1e-4, atol=1e-5)
+    sel, idx = sim.select(pop, k=12)
+    vals = cr.gebv(germ, sim.GEBV_model.marker_effects).sum(-1).astype(np.float32)
+    _, ref_idx = jp.top_k(vals, 12)
+    assert np.array_equal(idx, ref_idx) and np.array_equal(np.asarray(sel), germ[ref_idx])
+    assert np.array_equal(sim._diallel_indices(np.array([4, 2, 9])), cr.diallel_indices(np.array([4, 2, 9])))
+
+
+def test_wheat_breedgym_shapes(cuda_device):
+    from breedgym_b200.vector import VecBreedGym, WheatBreedGym
+
+    n = 40
+    env = WheatBreedGym(VecBreedGym(num_envs=2, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n,
+                                    autoreset=False),
+                        n_lines=12, plant_per_line=10, k_per_line=5)
+    _, infos = env.reset(seed=0)
+    for _ in range(10):
+        pop, rews, _, tru, infos = env.step(np.random.rand(2, 12, 12))
+        assert pop.shape == (2, n, 1000, 2) and infos["GEBV"].shape == (2, n, 1)
+    assert np.all(tru) and np.all(rews != 0)
+    got = np.asarray(pop)
+    assert np.array_equal(got[..., 0], got[..., 1])  # double haploids are homozygous

@@ -1,0 +1,147 @@
+"""The oracle against every known answer available for this path (CPU only).
+
+The reference's own tests hold no golden vector that can be evaluated here (their
+inputs come from `chromax.sample_data`, absent); what exists: the Random123
+Threefry vectors, the values JAX documents for key(0), and this repo's committed
+self-pins (tests/golden).
+"""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import chromax_ref as cr
+from oracle import jax_prng as jp
+
+KATS = [
+    ((0x00000000, 0x00000000), (0x00000000, 0x00000000), (0x6B200159, 0x99BA4EFE)),
+    ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+    ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0)),
+]
+
+
+@pytest.mark.parametrize("key,ctr,expect", KATS)
+def test_threefry_random123_vectors(key, ctr, expect):
+    a, b = jp.threefry2x32(key[0], key[1], ctr[0], ctr[1])
+    assert (int(a), int(b)) == expect
+    assert co.threefry2x32(key[0], key[1], ctr[0], ctr[1]) == expect
+
+
+def test_jax_documented_values_legacy():
+    # jax.random.split(jax.random.PRNGKey(0)) and uniform(PRNGKey(0)) with the pre-0.5 default layout
+    assert jp.split(jp.key(0), 2, "legacy").tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert np.float32(jp.uniform(jp.key(0), 1, "legacy")[0]) == np.float32(0.41845703)
+
+
+def test_jax_documented_values_partitionable():
+    assert jp.split(jp.key(0), 2, "partitionable").tolist() == [[1797259609, 2579123966], [928981903, 3453687069]]
+    assert abs(float(jp.uniform(jp.key(0), 1, "partitionable")[0]) - 0.947667) < 1e-6
+
+
+def test_key_of_wide_seed():
+    assert jp.key(7).tolist() == [0, 7]
+    assert jp.key((5 << 32) + 9).tolist() == [5, 9]
+
+
+@pytest.mark.parametrize("layout", jp.LAYOUTS)
+def test_c_and_numpy_prng_agree(layout):
+    for n in (1, 2, 3, 8, 33, 1000, 1001):
+        assert np.array_equal(co.random_bits(jp.key(5), n, layout), jp.random_bits(jp.key(5), n, layout))
+        assert np.array_equal(co.split(jp.key(5), n, layout), jp.split(jp.key(5), n, layout))
+
+
+def test_threshold_equivalence_sampled():
+    """u < r  <=>  (bits >> 9) < ceil(r 2^23): checked on random bits x awkward thresholds."""
+    rng = np.random.default_rng(0)
+    bits = rng.integers(0, 2**32, 200000, dtype=np.uint64).astype(np.uint32)
+    rs = np.array([0.0, 1e-9, 2.0**-23, 2.0**-23 * 1.5, 1.5e-3, 0.1, 0.25 + 2**-24, 0.5, 0.999999, 1.0, 1.5, -0.1],
+                  dtype=np.float32)
+    u = jp.bits_to_uniform(bits)
+    for r in rs:
+        t = jp.threshold_u32(np.array([r]))[0]
+        assert np.array_equal(u < r, (bits >> np.uint32(9)) < t), r
+
+
+def test_permutation_is_permutation_and_rounds():
+    assert jp.shuffle_rounds(370) == 1 and jp.shuffle_rounds(1625) == 1 and jp.shuffle_rounds(1626) == 2
+    for layout in jp.LAYOUTS:
+        p = jp.permutation(jp.key(3), 2000, layout)
+        assert sorted(p.tolist()) == list(range(2000))
+
+
+def test_repeat_total_semantics():
+    x = np.arange(6).reshape(3, 2)
+    assert jp.repeat_total(x, 2, 4).tolist() == [[0, 1], [0, 1], [2, 3], [2, 3]]
+    assert jp.repeat_total(x, 1, 5).tolist() == [[0, 1], [2, 3], [4, 5], [4, 5], [4, 5]]
+    assert jp.repeat_total(x, np.array([0, 3, 1]), 4).tolist() == [[2, 3], [2, 3], [2, 3], [4, 5]]
+
+
+def test_top_k_ties_take_lower_index():
+    v, i = jp.top_k(np.array([1.0, 3.0, 3.0, 2.0, 3.0]), 3)
+    assert i.tolist() == [1, 2, 4] and v.tolist() == [3.0, 3.0, 3.0]
+
+
+def test_golden_fixtures_reproduce(golden):
+    g = golden
+    pop, pairs, r, eff, key = g["pop"], g["pairs"], g["r"], g["eff"], g["key"]
+    for lay in jp.LAYOUTS:
+        for sch in cr.SCHEDULES:
+            off = cr.cross(pop[pairs], r, key, 0.0, sch, lay)
+            assert np.array_equal(off, g[f"cross_{lay}_{sch}"])
+            assert np.array_equal(co.cross_envs(pop[None], pairs[None], r, key, 0.0, sch, lay)[0], off)
+            assert np.allclose(cr.gebv(off, eff), g[f"gebv_{lay}_{sch}"], rtol=1e-12, atol=0)
+        assert np.array_equal(cr.cross(pop[pairs], r, key, 0.05, "S2", lay), g[f"cross_mut_{lay}"])
+        assert np.array_equal(co.cross_envs(pop[None], pairs[None], r, key, 0.05, "S2", lay)[0], g[f"cross_mut_{lay}"])
+        assert np.array_equal(cr.double_haploid(pop, r, key, 3, 0.0, "S2", lay), g[f"dh_{lay}"])
+        rk, _, idx = cr.vec_reset(np.zeros((50, 1, 2), bool), 20, 3, jp.key(7), lay)
+        assert np.array_equal(idx, g[f"reset_idx_{lay}"]) and np.array_equal(rk, g[f"reset_key_{lay}"])
+        assert np.array_equal(jp.permutation(jp.key(11), 2000, lay), g[f"perm2000_{lay}"])
+    # different layouts / schedules really are different streams
+    assert not np.array_equal(g["cross_legacy_S1"], g["cross_legacy_S2"])
+    assert not np.array_equal(g["cross_legacy_S2"], g["cross_partitionable_S2"])
+
+
+def test_meiosis_structure():
+    """r = 0 everywhere but the first marker: the gamete is one whole parental haplotype."""
+    rng = np.random.default_rng(1)
+    ind = rng.random((501, 2)) < 0.5
+    r = np.zeros(501, np.float32)
+    r[0] = 0.5
+    seen = set()
+    for s in range(16):
+        hap = cr.meiosis(ind, r, jp.key(s))
+        which = 0 if np.array_equal(hap, ind[:, 0]) else 1
+        assert np.array_equal(hap, ind[:, which])
+        seen.add(which)
+    assert seen == {0, 1}
+
+
+def test_vec_step_shares_masks_across_envs():
+    """All envs see the same crossover mask (reference vmap quirk): with identical
+    populations and actions every env produces identical offspring."""
+    rng = np.random.default_rng(2)
+    pop = rng.random((7, 130, 2)) < 0.5
+    pops = np.stack([pop, pop, pop])
+    act = np.tile(rng.integers(0, 7, (1, 5, 2)), (3, 1, 1))
+    r = np.full(130, 0.05, np.float32)
+    sim = cr.OracleSimulator(r, np.ones((130, 1), np.float32), seed=3)
+    out = cr.vec_step(sim, pops, act)
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+
+
+def test_recombination_vector_from_map_files():
+    from pathlib import Path
+
+    DATA = Path(__file__).resolve().parents[1] / "breedgym_b200" / "data"
+    gm = cr.read_genetic_map(DATA / "small_genetic_map.txt")
+    r = cr.recombination_vector(gm)
+    lens = cr.chr_lens(gm)
+    assert lens.tolist() == [1543, 1235, 1108, 956, 1204, 800, 831, 891, 714, 718]
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    assert np.all(r[starts] == 0.5) and r.dtype == np.float32
+    raw = gm["RecombRate"].to_numpy()
+    j = 5
+    assert r[j] == np.float32(raw[j - 1])  # shifted by one marker
+    wheat = cr.read_genetic_map(DATA / "wheat_genetic_map.csv")
+    rw = cr.recombination_vector(wheat)
+    assert len(cr.chr_lens(wheat)) == 21 and rw.max() <= 0.5 and rw.min() >= 0.0
+    assert len(cr.trait_columns(wheat)) == 7
