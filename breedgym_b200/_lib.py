@@ -22,6 +22,8 @@ _ERRORS = {-1: ValueError, -2: RuntimeError, -3: MemoryError, -4: ValueError, -5
 _SIGNATURES = {
     "bg_version": (c_int, []),
     "bg_last_error": (c_char_p, []),
+    "bg_kernel_launches": (c_int64, []),
+    "bg_blend_envs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "bg_threefry2x32": (None, [c_uint32, c_uint32, c_uint32, c_uint32, c_void_p]),
     "bg_key_split": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
     "bg_random_bits": (c_int, [c_void_p, c_int64, c_int, c_void_p]),

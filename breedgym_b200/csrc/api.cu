@@ -8,6 +8,7 @@
 #include "threefry.cuh"
 
 static thread_local std::string g_err;
+std::atomic<long long> bg_launch_counter{0};
 
 void bg_set_error(const std::string &msg) { g_err = msg; }
 
@@ -63,6 +64,7 @@ struct DeviceGuard {
 extern "C" {
 
 int bg_version(void) { return BG_VERSION; }
+int64_t bg_kernel_launches(void) { return (int64_t)bg_launch_counter.load(std::memory_order_relaxed); }
 const char *bg_last_error(void) { return g_err.c_str(); }
 
 void bg_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t out[2])
@@ -253,6 +255,16 @@ int bg_cross(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32
                                 eng->mut_thr ? eng->d_mut : nullptr, nullptr, nullptr, 0, 0, nullptr, st);
     if (rc) return rc;
     return bg_launch_blend(eng, pop, parents, eng->d_mask, eng->mut_thr ? eng->d_mut : nullptr, out, E, n_src, n, st);
+}
+
+int bg_blend_envs(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, const uint32_t *mut,
+                  uint32_t *out, int64_t E, int64_t n_src, int64_t n, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(eng->m > 0, BG_ESTATE, "engine has no map (call bg_engine_set_map)");
+    BG_REQUIRE(E >= 0 && n >= 0 && n_src > 0, BG_EINVAL, "bg_blend_envs: bad shape");
+    BG_REQUIRE(E * n == 0 || (pop && parents && mask && out), BG_EINVAL, "bg_blend_envs: null buffer");
+    return bg_launch_blend(eng, pop, parents, mask, mut, out, E, n_src, n, (cudaStream_t)stream);
 }
 
 int bg_double_haploid(bg_engine *eng, const uint32_t *pop, uint32_t *out, int64_t n, int64_t n_offspring,

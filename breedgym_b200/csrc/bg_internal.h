@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 #include "../../include/breedgym_b200.h"
@@ -37,6 +38,14 @@ int bg_cuda_fail(cudaError_t e, const char *what);
     do {                                                    \
         cudaError_t e__ = (call);                           \
         if (e__ != cudaSuccess) return bg_cuda_fail(e__, #call); \
+    } while (0)
+
+// after every kernel launch: count it (bg_kernel_launches) and surface launch errors
+extern std::atomic<long long> bg_launch_counter;
+#define BG_LAUNCHED()                                     \
+    do {                                                  \
+        bg_launch_counter.fetch_add(1, std::memory_order_relaxed); \
+        BG_CUDA(cudaGetLastError());                      \
     } while (0)
 
 #define BG_REQUIRE(cond, code, msg) \

@@ -134,9 +134,9 @@ int bg_launch_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out
         const int wpb = 8;
         gebv_direct_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(pop, rows, eng->W, eng->Wpad, eng->d_wfix, T,
                                                                                   mpad, eng->d_acc);
-        BG_CUDA(cudaGetLastError());
+        BG_LAUNCHED();
         gebv_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(eng->d_acc, eng->d_inv_scale, T, total, out, false);
-        BG_CUDA(cudaGetLastError());
+        BG_LAUNCHED();
         return BG_OK;
     }
     BG_REQUIRE(T <= 65535, BG_ELIMIT, "too many traits for the LUT kernel grid");
@@ -154,9 +154,9 @@ int bg_launch_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out
     BG_CUDA(cudaMemsetAsync(eng->d_acc, 0, (size_t)total * sizeof(unsigned long long), st));
     dim3 grid((unsigned)strips, (unsigned)ysplit, (unsigned)T);
     gebv_lut_kernel<<<grid, 256, smem, st>>>(pop, rows, eng->Wpad, eng->d_wfix, mpad, eng->d_acc, T, rows_per_cta);
-    BG_CUDA(cudaGetLastError());
+    BG_LAUNCHED();
     gebv_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(eng->d_acc, eng->d_inv_scale, T, total, out, false);
-    BG_CUDA(cudaGetLastError());
+    BG_LAUNCHED();
     return BG_OK;
 }
 
@@ -166,6 +166,6 @@ int bg_launch_reduce(const float *in, int64_t E, int64_t per_env, float *out, in
     BG_REQUIRE(per_env > 0, BG_EINVAL, "empty reduction");
     BG_REQUIRE(E < (int64_t(1) << 31), BG_ELIMIT, "too many envs");
     reduce_env_kernel<<<(unsigned)E, 256, 0, st>>>(in, per_env, out, op);
-    BG_CUDA(cudaGetLastError());
+    BG_LAUNCHED();
     return BG_OK;
 }

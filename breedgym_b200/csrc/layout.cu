@@ -118,7 +118,7 @@ int bg_launch_pack(const uint8_t *in, uint32_t *out, int64_t rows, int64_t m, in
     const int64_t blocks = (warps + 7) / 8;
     BG_REQUIRE(blocks < (int64_t(1) << 31), BG_ELIMIT, "pack grid too large");
     pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, rows, m, W, Wpad);
-    BG_CUDA(cudaGetLastError());
+    BG_LAUNCHED();
     return BG_OK;
 }
 
@@ -129,7 +129,7 @@ int bg_launch_unpack(const uint32_t *in, uint8_t *out, int64_t rows, int64_t m, 
     BG_REQUIRE(zs <= 65535, BG_ELIMIT, "unpack grid too large");
     dim3 grid((unsigned)((m + 255) / 256), (unsigned)(rows < 65535 ? rows : 65535), (unsigned)zs);
     unpack_kernel<<<grid, 256, 0, st>>>(in, out, rows, m, Wpad);
-    BG_CUDA(cudaGetLastError());
+    BG_LAUNCHED();
     return BG_OK;
 }
 
@@ -139,7 +139,7 @@ int bg_launch_gather(const uint32_t *src, const int32_t *idx, uint32_t *dst, int
     if (E * n == 0) return BG_OK;
     BG_REQUIRE(E * n < (int64_t(1) << 31), BG_ELIMIT, "gather grid too large");
     gather_kernel<<<(unsigned)(E * n), 128, 0, st>>>((const uint4 *)src, idx, (uint4 *)dst, n_src, n, src_env_rows, 2 * Wpad / 4);
-    BG_CUDA(cudaGetLastError());
+    BG_LAUNCHED();
     return BG_OK;
 }
 
@@ -157,6 +157,6 @@ int bg_launch_reset_indices(bg_engine *eng, const uint32_t key[2], int64_t E_tot
     auto kern = layout == BG_LAYOUT_LEGACY ? reset_indices_kernel<BG_LAYOUT_LEGACY> : reset_indices_kernel<BG_LAYOUT_PARTITIONABLE>;
     if (smem > 48 * 1024) BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)E, 256, smem, st>>>(key[0], key[1], E_total, env_begin, (int)N, (int)n, rounds, idx_out);
-    BG_CUDA(cudaGetLastError());
+    BG_LAUNCHED();
     return BG_OK;
 }

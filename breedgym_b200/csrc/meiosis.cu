@@ -323,7 +323,7 @@ int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_
     auto kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE>;
     if (smem > 48 * 1024) BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)rows, NT, smem, st>>>(P);
-    BG_CUDA(cudaGetLastError());
+    BG_LAUNCHED();
     return BG_OK;
 }
 
@@ -353,6 +353,6 @@ int bg_launch_blend(bg_engine *eng, const uint32_t *pop, const int32_t *parents,
     else
         blend_envs_kernel<false><<<grid, threads, 0, st>>>((const uint4 *)pop, parents, (const uint4 *)mask, nullptr,
                                                            (uint4 *)out, (int)E, n_src, rows, W4, chunk);
-    BG_CUDA(cudaGetLastError());
+    BG_LAUNCHED();
     return BG_OK;
 }

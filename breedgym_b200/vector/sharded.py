@@ -83,9 +83,14 @@ class ShardedVecBreedGym:
     def step(self, local_actions):
         will_reward = self.env.reward_shaping or self.env.step_idx + 1 == self.env.num_generations
         obs, rews, ter, tru, infos = self.env.step(local_actions)
+        on_device = isinstance(rews, torch.Tensor)  # info_device="device": rewards never leave the GPUs
         if will_reward:
-            local = torch.from_numpy(np.ascontiguousarray(rews, dtype=np.float32)).to(self.env.device)
-            rews = allgather_rewards(local, self.counts, self.group).cpu().numpy()
+            local = rews if on_device else torch.from_numpy(np.ascontiguousarray(rews, dtype=np.float32)).to(self.env.device)
+            rews = allgather_rewards(local, self.counts, self.group)
+            if not on_device:
+                rews = rews.cpu().numpy()
+        elif on_device:
+            rews = torch.zeros(self.total_envs, dtype=torch.float32, device=self.env.device)
         else:
             rews = np.zeros(self.total_envs)
         ter = np.full(self.total_envs, bool(ter[0]) if len(ter) else False)

@@ -126,7 +126,7 @@ class VecBreedGym(VectorEnv):
         gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
         rew_dev = torch.empty((E,), dtype=torch.float32, device=self.device) if need_reward else None
         gebv_pin = self._pinned_buf("gebv", (E, n, T), torch.float32) if host_info else None
-        rew_pin = self._pinned_buf("rews", (E,), torch.float32) if need_reward else None
+        rew_pin = self._pinned_buf("rews", (E,), torch.float32) if (need_reward and host_info) else None
 
         k = np.ascontiguousarray(sim._next_key(), dtype=np.uint32)
         _lib.check(_lib.load().bg_vec_step(
@@ -134,9 +134,9 @@ class VecBreedGym(VectorEnv):
             _lib.nptr(k), sim._layout(), sim._schedule(), gebv_dev.data_ptr(),
             rew_dev.data_ptr() if need_reward else None,
             gebv_pin.data_ptr() if host_info else None,
-            rew_pin.data_ptr() if need_reward else None,
+            rew_pin.data_ptr() if rew_pin is not None else None,
             sim._stream()))
-        if act_host_ptr is not None and not (host_info or need_reward):  # no sync happened inside the call
+        if act_host_ptr is not None and not host_info:  # no sync happened inside the call
             self._h2d_done = torch.cuda.Event()
             self._h2d_done.record(torch.cuda.current_stream(self.device))
         else:
@@ -145,7 +145,10 @@ class VecBreedGym(VectorEnv):
         self.step_idx += 1
 
         infos = {"GEBV": gebv_pin.numpy().copy() if host_info else gebv_dev}
-        rews = rew_pin.numpy().copy() if need_reward else np.zeros(E)
+        if host_info:
+            rews = rew_pin.numpy().copy() if need_reward else np.zeros(E)
+        else:  # device mode: nothing leaves the GPU, nothing synchronises
+            rews = rew_dev if need_reward else torch.zeros(E, dtype=torch.float32, device=self.device)
 
         if done and self.autoreset:
             self.reset()

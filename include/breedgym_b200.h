@@ -50,6 +50,8 @@ extern "C" {
 typedef struct bg_engine bg_engine;
 
 int bg_version(void);
+/* number of CUDA kernels this library has launched in this process (monotonic) */
+int64_t bg_kernel_launches(void);
 const char *bg_last_error(void);
 
 /* ---- host-side PRNG helpers (no GPU touched) ------------------------------
@@ -100,6 +102,12 @@ int bg_gather_individuals(bg_engine *eng, const uint32_t *src, const int32_t *id
  * blends all envs against them. */
 int bg_cross(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src,
              int64_t n, const uint32_t cross_key[2], int layout, int schedule, void *stream);
+
+/* second half of the E > 1 path of bg_cross on its own: blend every env against
+ * precomputed masks (mask / mut: packed [2n][Wpad] from bg_meiosis_masks; mut may
+ * be NULL).  Same reference interface as bg_cross (vec_env.py:75-77,89-91). */
+int bg_blend_envs(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, const uint32_t *mut,
+                  uint32_t *out, int64_t E, int64_t n_src, int64_t n, void *stream);
 
 /* chromax: Simulator.double_haploid / functional.double_haploid
  * (breedgym/vector/breeding_programs_env.py:41).  pop packed [n][2][Wpad] ->
