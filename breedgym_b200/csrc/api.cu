@@ -203,6 +203,36 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
         BG_CUDA(cudaMemcpy(eng->d_wfix, wfix.data(), wfix.size() * sizeof(long long), cudaMemcpyHostToDevice));
         BG_CUDA(cudaMalloc(&eng->d_inv_scale, n_traits * sizeof(double)));
         BG_CUDA(cudaMemcpy(eng->d_inv_scale, inv.data(), n_traits * sizeof(double), cudaMemcpyHostToDevice));
+
+        // tensor-core digit table: w_fix = sum_d digit_d * 256^d with balanced digits in [-128,127],
+        // stored per 128-marker step as [N/8][8][8 rows][16 B] core matrices (gebv_tc*.cu).  Inside
+        // a 32-marker word, K index 4*s + b holds marker 8*b + s (matches the kernels' expansion).
+        eng->tc_N = 0;
+        eng->tc_steps = 0;
+        if (n_traits <= bg_gebv_tc_max_traits()) {
+            const int N = ((8 * n_traits + 15) / 16) * 16;
+            const int64_t steps = eng->Wpad / 4;
+            std::vector<signed char> dig((size_t)(steps + 1) * N * 128, 0);  // one zero step of slack
+            for (int t = 0; t < n_traits; ++t)
+                for (int64_t j = 0; j < n_markers; ++j) {
+                    long long w = wfix[t * stride + j];
+                    if (w == 0) continue;
+                    const int64_t st = j / 128;
+                    const int word = (int)(j % 128) / 32, bit = (int)(j % 32);
+                    const int k = word * 32 + 4 * (bit % 8) + bit / 8;
+                    for (int d = 0; d < 8; ++d) {
+                        const int dgt = (int)(((w + 128) & 255) - 128);
+                        w = (w - dgt) >> 8;
+                        const int n = 8 * t + d;
+                        const size_t off = (((size_t)st * (N / 8) + n / 8) * 8 + k / 16) * 128 + (n % 8) * 16 + k % 16;
+                        dig[off] = (signed char)dgt;
+                    }
+                }
+            BG_CUDA(cudaMalloc(&eng->d_wdig, dig.size()));
+            BG_CUDA(cudaMemcpy(eng->d_wdig, dig.data(), dig.size(), cudaMemcpyHostToDevice));
+            eng->tc_N = N;
+            eng->tc_steps = steps;
+        }
     }
     return BG_OK;
 }

@@ -21,8 +21,9 @@ struct bg_engine {
     uint32_t mut_thr = 0;             // mutation threshold (0 = off)
     long long *d_wfix = nullptr;      // [T][Wpad*32] fixed-point effects (zero padded)
     double *d_inv_scale = nullptr;    // [T] 2^-s_t
-    signed char *d_wdig = nullptr;    // [T*8][Kpad] int8 base-256 digits (tensor-core GEBV)
-    int64_t Kpad = 0;
+    signed char *d_wdig = nullptr;    // [tc_steps][tc_N/8][8][8][16] int8 base-256 digits in core-matrix order
+    int64_t tc_steps = 0;             // 128-marker K steps (= Wpad / 4)
+    int32_t tc_N = 0;                 // 8*T rounded up to a multiple of 16 (0: tensor-core path unavailable)
     // grow-only scratch
     uint32_t *d_mask = nullptr;
     uint32_t *d_mut = nullptr;
@@ -70,6 +71,12 @@ int bg_launch_blend(bg_engine *eng, const uint32_t *pop, const int32_t *parents,
 // gebv.cu
 int bg_launch_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, int algo, cudaStream_t st);
 int bg_launch_reduce(const float *in, int64_t E, int64_t per_env, float *out, int op, cudaStream_t st);
+
+// gebv_tc.cu
+int bg_gebv_tc_max_traits(void);
+int bg_launch_gebv_tc(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st);
+// gebv_tc2.cu: TMA tile loads + operand A in tensor memory
+int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st);
 
 // layout.cu
 int bg_launch_pack(const uint8_t *in, uint32_t *out, int64_t rows, int64_t m, int W, int Wpad, cudaStream_t st);

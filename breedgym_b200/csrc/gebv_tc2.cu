@@ -1,0 +1,331 @@
+// GEBV on tcgen05, second generation: TMA tile loads + the dosage operand in TENSOR MEMORY.
+//
+// Same exact int8 GEMM as gebv_tc.cu (D[i, 8t+d] = sum_j dosage[i,j] * digit_d(w_fix[j,t]),
+// replaces chromax TraitModel.__call__, breedgym/breedgym.py:233, vec_env.py:132-134), but the
+// 128 x K dosage operand never touches shared memory:
+//
+//   warp 8  (loader, 2 lanes) : lane 0 streams raw bit-plane tiles [256 plane-rows x 16 B] with
+//                               cp.async.bulk.tensor.2d (a tensor map over the packed population),
+//                               lane 1 streams the digit tiles with 1-D bulk copies; both land on
+//                               mbarriers with expect_tx, nothing sits on a thread's scoreboard.
+//   warps 0-7 (expanders)     : two groups of 128 threads take alternate 128-marker steps; thread t
+//                               <-> individual t of the tile <-> TMEM lane t.  4 words per plane ->
+//                               128 dosage bytes by shift/mask/add -> 4 x tcgen05.st.32x32b.x8
+//                               straight into the A stage in tensor memory.
+//   warp 9  (MMA, 1 lane)     : 4 x tcgen05.mma.kind::i8 per step with A from TMEM, B (digits) from
+//                               shared memory, D in TMEM; tcgen05.commit frees the A/B stage.
+//   warps 0-3 (epilogue)      : tcgen05.ld, digits -> int64 partial sums.
+//
+// Per CTA: 22 KB of shared memory and 128 TMEM columns for <= 4 traits => 4 CTAs (40 warps) per SM.
+#include <cuda.h>
+
+#include "bg_internal.h"
+
+namespace {
+
+constexpr int T2_M = 128;
+constexpr int T2_KS = 128;          // markers per step (4 words per plane, 32 TMEM columns of int8x4)
+constexpr int T2_S = 3;             // A (TMEM) / B (smem) stages
+constexpr int T2_R = 4;             // raw tile ring
+constexpr int T2_THREADS = 256 + 64;
+constexpr uint32_t T2_RAW_BYTES = 2 * T2_M * 16;  // 256 plane-rows x 16 B
+constexpr uint32_t T2_SPIN_LIMIT = 1u << 28;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > T2_SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&o)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(o[0]), "r"(o[1]),
+                 "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                 : "memory");
+}
+
+struct T2Bars {
+    uint64_t raw_full[T2_R], raw_empty[T2_R];
+    uint64_t a_full[T2_S], a_empty[T2_S], b_full[T2_S];
+    uint64_t done;
+};
+
+// smem: raw ring [T2_R][256 plane-rows][16 B], then B stages [T2_S][N/8][8 ki][8][16 B]
+__global__ void __launch_bounds__(T2_THREADS) gebv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, int64_t rows,
+                                                              const int8_t *__restrict__ bdig, int N, int T, int steps_total,
+                                                              int steps_per_split, long long *__restrict__ partial)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) T2Bars bars;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw_base = smem_u32(smem);
+    const uint32_t b_bytes = (uint32_t)N * T2_KS;
+    const uint32_t b_base0 = raw_base + T2_R * T2_RAW_BYTES;
+    const int64_t row0 = (int64_t)blockIdx.x * T2_M;
+    const int s_begin = blockIdx.y * steps_per_split;
+    const int nst = min(steps_total, s_begin + steps_per_split) - s_begin;
+
+    uint32_t d_cols = 32;
+    while ((int)d_cols < N) d_cols <<= 1;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < d_cols + T2_S * (T2_KS / 4)) tmem_cols <<= 1;
+
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < T2_R; ++i) {
+            mbar_init(smem_u32(&bars.raw_full[i]), 1);   // expect_tx arrival of the loader
+            mbar_init(smem_u32(&bars.raw_empty[i]), 4);  // the 4 warps of the group that read the tile
+        }
+        for (int i = 0; i < T2_S; ++i) {
+            mbar_init(smem_u32(&bars.a_full[i]), 4);   // the 4 warps of the group that filled the stage
+            mbar_init(smem_u32(&bars.a_empty[i]), 1);  // tcgen05.commit
+            mbar_init(smem_u32(&bars.b_full[i]), 1);   // expect_tx arrival of the loader
+        }
+        mbar_init(smem_u32(&bars.done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+    const uint32_t tmem_a = tmem_d + d_cols;
+
+    if (warp < 8) {
+        // ---------------- expanders: group g takes steps j with j % 2 == g ----------------
+        const int g = warp >> 2, r = tid & (T2_M - 1);
+        const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quadrant
+        for (int j = g; j < nst; j += 2) {
+            const int rs = j % T2_R, as = j % T2_S;
+            mbar_wait(smem_u32(&bars.raw_full[rs]), (j / T2_R) & 1);
+            const uint32_t src = raw_base + rs * T2_RAW_BYTES + (uint32_t)r * 32;  // [row][plane][16 B]
+            const uint4 x0 = lds128(src), x1 = lds128(src + 16);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[rs]));
+            if (j >= T2_S) mbar_wait(smem_u32(&bars.a_empty[as]), ((j / T2_S) - 1) & 1);  // MMAs of the previous use retired
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t w0[4] = {x0.x, x0.y, x0.z, x0.w}, w1[4] = {x1.x, x1.y, x1.z, x1.w};
+            const uint32_t ta = tmem_a + lane_sel + (uint32_t)as * (T2_KS / 4);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                uint32_t o[8];
+#pragma unroll
+                for (int sft = 0; sft < 8; ++sft)  // column sft, byte b <-> K index 4*sft + b <-> marker 8b + sft of this word
+                    o[sft] = ((w0[jj] >> sft) & 0x01010101u) + ((w1[jj] >> sft) & 0x01010101u);
+                tmem_st8(ta + 8 * jj, o);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[as]));
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            // ---------------- raw bit-plane tiles (TMA 2-D) ----------------
+            const int y = (int)(2 * row0);  // plane-row coordinate
+            for (int j = 0; j < nst; ++j) {
+                const int rs = j % T2_R;
+                if (j >= T2_R) mbar_wait(smem_u32(&bars.raw_empty[rs]), ((j / T2_R) - 1) & 1);
+                const uint32_t full = smem_u32(&bars.raw_full[rs]);
+                mbar_arrive_expect_tx(full, T2_RAW_BYTES);
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                        raw_base + rs * T2_RAW_BYTES),
+                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((s_begin + j) * 4), "r"(y), "r"(full)
+                    : "memory");
+            }
+        } else if (lane == 1) {
+            // ---------------- digit tiles (1-D bulk copies) ----------------
+            for (int j = 0; j < nst; ++j) {
+                const int bs = j % T2_S;
+                if (j >= T2_S) mbar_wait(smem_u32(&bars.a_empty[bs]), ((j / T2_S) - 1) & 1);
+                const uint32_t full = smem_u32(&bars.b_full[bs]);
+                mbar_arrive_expect_tx(full, b_bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 b_base0 + bs * b_bytes),
+                             "l"(bdig + (int64_t)(s_begin + j) * b_bytes), "r"(b_bytes), "r"(full)
+                             : "memory");
+            }
+        }
+    } else if (lane == 0) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T2_M >> 4) << 24);
+        for (int j = 0; j < nst; ++j) {
+            const int as = j % T2_S;
+            const uint32_t par = (j / T2_S) & 1;
+            mbar_wait(smem_u32(&bars.b_full[as]), par);
+            mbar_wait(smem_u32(&bars.a_full[as]), par);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int kk = 0; kk < T2_KS / 32; ++kk) {
+                const uint32_t a_taddr = tmem_a + (uint32_t)as * (T2_KS / 4) + 8 * kk;
+                const uint64_t bdesc = make_smem_desc(b_base0 + as * b_bytes + kk * 256, 128, 1024);
+                const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                    ::"r"(tmem_d), "r"(a_taddr), "l"(bdesc), "r"(idesc), "r"(acc)
+                    : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars.a_empty[as]))
+                         : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars.done))
+                     : "memory");
+    }
+
+    if (warp < 4) {  // epilogue: thread t <-> accumulator row t <-> TMEM lane t
+        mbar_wait(smem_u32(&bars.done), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t row = row0 + tid;
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+        long long *dst = partial + ((int64_t)blockIdx.y * rows + row) * T;
+        for (int t = 0; t < T; ++t) {
+            uint32_t v[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                         : "r"(taddr + (uint32_t)(8 * t))
+                         : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            unsigned long long sum = 0;  // modular arithmetic: the true total fits in int64
+#pragma unroll
+            for (int d = 7; d >= 0; --d) sum = (sum << 8) + (unsigned long long)(long long)(int32_t)v[d];
+            if (row < rows) dst[t] = (long long)sum;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 9)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+}
+
+__global__ void gebv_tc2_finalize_kernel(const long long *__restrict__ partial, int ksplit, int64_t total,
+                                         const double *__restrict__ inv_scale, int T, float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    long long s = 0;
+    for (int k = 0; k < ksplit; ++k) s += partial[(int64_t)k * total + i];
+    out[i] = (float)((double)s * inv_scale[i % T]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st)
+{
+    BG_REQUIRE(eng && eng->d_wdig, BG_ESTATE, "engine has no tensor-core digit table");
+    const int T = eng->T, N = eng->tc_N;
+    const int steps = (int)eng->tc_steps;
+    const int64_t tiles = (rows + T2_M - 1) / T2_M;
+    BG_REQUIRE(tiles < (int64_t(1) << 31) && 2 * rows < (int64_t(1) << 31), BG_ELIMIT, "too many rows");
+    EncodeTiledFn enc = encode_tiled();
+    BG_REQUIRE(enc, BG_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+
+    // 2-D view of the packed population: [2*rows plane-rows][Wpad words]; box = 4 words x 256 plane-rows
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)eng->Wpad, (cuuint64_t)(2 * rows)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)eng->Wpad * 4};
+    const cuuint32_t box[2] = {4, 2 * T2_M};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t *>(pop), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BG_REQUIRE(cr == CUDA_SUCCESS, BG_ECUDA, "cuTensorMapEncodeTiled failed");
+
+    const size_t smem = (size_t)T2_R * T2_RAW_BYTES + (size_t)T2_S * N * T2_KS;
+    BG_REQUIRE(smem <= (size_t)eng->max_smem_optin, BG_ELIMIT, "too many traits for the tensor-core GEBV tile");
+    // residency: TMEM columns (512 per SM) and shared memory
+    uint32_t d_cols = 32;
+    while ((int)d_cols < N) d_cols <<= 1;
+    uint32_t tcols = 32;
+    while (tcols < d_cols + T2_S * (T2_KS / 4)) tcols <<= 1;
+    int resident = (int)(512 / tcols);
+    const int by_smem = (int)(227 * 1024 / (smem + 1024));
+    if (by_smem < resident) resident = by_smem;
+    if (resident > 6) resident = 6;  // 10 warps per CTA, 64 per SM
+    if (resident < 1) resident = 1;
+    int64_t target = (int64_t)resident * eng->sm_count;  // one full wave
+    if (const char *s = getenv("BG_TC_TARGET_CTAS")) target = atoll(s) > 0 ? atoll(s) : target;
+    int ksplit = (int)(target / tiles);
+    const int max_split = (steps + 7) / 8;
+    if (ksplit > max_split) ksplit = max_split;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > 65535) ksplit = 65535;
+    const int sps = (steps + ksplit - 1) / ksplit;
+    ksplit = (steps + sps - 1) / sps;
+    const int64_t total = rows * T;
+    int rc = bg_reserve_acc(eng, (size_t)total * ksplit);
+    if (rc) return rc;
+    if (smem > 48 * 1024)
+        BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)tiles, (unsigned)ksplit);
+    gebv_tc2_kernel<<<grid, T2_THREADS, smem, st>>>(tmap, rows, eng->d_wdig, N, T, steps, sps,
+                                                    reinterpret_cast<long long *>(eng->d_acc));
+    BG_LAUNCHED();
+    gebv_tc2_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long *>(eng->d_acc), ksplit,
+                                                                             total, eng->d_inv_scale, T, out);
+    BG_LAUNCHED();
+    return BG_OK;
+}

@@ -129,7 +129,9 @@ int bg_meiosis_masks(bg_engine *eng, uint32_t *mask_out, int64_t rows, const uin
  * to float32 (deterministic; differs from a float64 dot by < 1 ulp of float32). */
 int bg_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, void *stream);
 /* same result through the straightforward bit-test kernel (cross-check / fallback
- * shapes); algorithm id for bg_gebv: 0 auto, 1 direct, 2 byte-LUT */
+ * shapes); algorithm id: 0 auto, 1 direct bit-test, 2 byte-LUT, 3 tcgen05 int8 GEMM
+ * (TMA loads, dosage operand in tensor memory), 4 tcgen05 int8 GEMM (operand staged in shared
+ * memory).  All produce the same 64-bit integers. */
 int bg_gebv_algo(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, int algo, void *stream);
 
 /* rews = np.max(infos["GEBV"], axis=(1,2))  (breedgym/vector/vec_env.py:97):

@@ -280,7 +280,7 @@ def gebv_algo(sim, packed, algo):
 
 
 @pytest.mark.parametrize("m,T,rows", [(1, 1, 3), (33, 2, 5), (128, 1, 4), (129, 3, 300), (1000, 7, 64), (10000, 1, 700),
-                                      (100002, 1, 40)])
+                                      (100002, 1, 40), (2500, 16, 130), (777, 32, 257)])
 def test_gebv_matches_float64_oracle(cuda_device, m, T, rows):
     rng = np.random.default_rng(m * 7 + T)
     df = make_map(m, T=T, seed=m)
@@ -289,8 +289,10 @@ def test_gebv_matches_float64_oracle(cuda_device, m, T, rows):
     packed = sim.as_packed(pop)
     eff = sim.GEBV_model.marker_effects
     ref = cr.gebv(pop, eff)
-    direct, lut = gebv_algo(sim, packed, 1), gebv_algo(sim, packed, 2)
-    assert np.array_equal(direct, lut), "both kernels sum the same fixed-point integers"
+    direct, lut, tc = gebv_algo(sim, packed, 1), gebv_algo(sim, packed, 2), gebv_algo(sim, packed, 3)
+    assert np.array_equal(direct, lut), "both CUDA-core kernels sum the same fixed-point integers"
+    assert np.array_equal(direct, tc), "the tcgen05 int8 GEMM (operand in TMEM) reproduces the same integers"
+    assert np.array_equal(direct, gebv_algo(sim, packed, 4)), "and so does the shared-memory-operand variant"
     auto = sim.GEBV_model(packed).cpu().numpy()
     assert np.array_equal(auto, lut)
     assert np.allclose(auto, ref, rtol=GEBV_RTOL, atol=0)
