@@ -27,6 +27,7 @@ _SIGNATURES = {
     "bg_threefry2x32": (None, [c_uint32, c_uint32, c_uint32, c_uint32, c_void_p]),
     "bg_key_split": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
     "bg_random_bits": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
+    "bg_key_chain_next": (c_int, [c_void_p, c_int, c_void_p]),
     "bg_thresholds": (c_int, [c_void_p, c_int64, c_void_p]),
     "bg_words_per_row": (c_int64, [c_int64]),
     "bg_engine_create": (c_int, [c_int, POINTER(c_void_p)]),
@@ -36,6 +37,8 @@ _SIGNATURES = {
     "bg_unpack": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "bg_gather_individuals": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "bg_cross": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p]),
+    "bg_cross_gebv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p,
+                              c_void_p]),
     "bg_double_haploid": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "bg_meiosis_masks": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "bg_gebv": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
@@ -43,8 +46,8 @@ _SIGNATURES = {
     "bg_reduce_max": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "bg_reduce_mean": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "bg_reset_indices": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
-    "bg_vec_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int,
-                            c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bg_vec_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

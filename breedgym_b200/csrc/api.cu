@@ -2,6 +2,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <chrono>
+#include <cstdio>
 #include <vector>
 
 #include "bg_internal.h"
@@ -87,6 +89,22 @@ int bg_key_split(const uint32_t key[2], int64_t num, int layout, uint32_t *out)
     return BG_OK;
 }
 
+int bg_key_chain_next(uint32_t state[2], int layout, uint32_t out[4])
+{
+    BG_REQUIRE(state && out, BG_EINVAL, "bg_key_chain_next: bad argument");
+    BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
+    const TfKey cur = tf_make_key(state[0], state[1]);
+    const TfKey after = tf_split_at(cur, 0, 2, layout), k = tf_split_at(cur, 1, 2, layout);
+    const TfKey next_k = tf_split_at(after, 1, 2, layout);
+    state[0] = after.k0;
+    state[1] = after.k1;
+    out[0] = k.k0;
+    out[1] = k.k1;
+    out[2] = next_k.k0;
+    out[3] = next_k.k1;
+    return BG_OK;
+}
+
 int bg_random_bits(const uint32_t key[2], int64_t n, int layout, uint32_t *out)
 {
     BG_REQUIRE(key && out && n >= 0, BG_EINVAL, "bg_random_bits: bad argument");
@@ -148,9 +166,20 @@ int bg_engine_destroy(bg_engine *eng)
     {
         DeviceGuard g(eng->device);
         free_map(eng);
-        cudaFree(eng->d_mask);
+        if (eng->side) {
+            cudaStreamSynchronize(eng->side);
+            cudaStreamDestroy(eng->side);
+        }
+        for (auto &sl : eng->slots) {
+            cudaFree(sl.mask);
+            cudaFree(sl.mut);
+            if (sl.ready) cudaEventDestroy(sl.ready);
+            if (sl.freed) cudaEventDestroy(sl.freed);
+        }
         cudaFree(eng->d_mut);
         cudaFree(eng->d_acc);
+        cudaFree(eng->d_acc2);
+        cudaFree(eng->d_tile_cnt);
     }
     delete eng;
     return BG_OK;
@@ -163,6 +192,8 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
     BG_REQUIRE(recomb && n_markers > 0 && n_markers < (int64_t(1) << 31) - 64, BG_EINVAL, "bad recombination vector");
     BG_REQUIRE(n_traits >= 0 && (n_traits == 0 || effects), BG_EINVAL, "bad marker effects");
     free_map(eng);
+    if (eng->side) BG_CUDA(cudaStreamSynchronize(eng->side));
+    for (auto &sl : eng->slots) sl.valid = false;  // masks depend on the thresholds
     eng->m = n_markers;
     eng->W = (int32_t)((n_markers + 31) / 32);
     eng->Wpad = (int32_t)bg_words_per_row(n_markers);
@@ -263,6 +294,112 @@ int bg_gather_individuals(bg_engine *eng, const uint32_t *src, const int32_t *id
     return bg_launch_gather(src, idx, dst, E, n_src, n, src_env_rows, eng->Wpad, (cudaStream_t)stream);
 }
 
+// ---- crossover-mask slots (vector env) ------------------------------------------------------
+static bool slot_matches(const bg_mask_slot &sl, const uint32_t key[2], int layout, int schedule, int64_t rows)
+{
+    return sl.valid && sl.key[0] == key[0] && sl.key[1] == key[1] && sl.layout == layout && sl.schedule == schedule &&
+           sl.rows == rows;
+}
+
+static int slot_prepare(bg_engine *eng, bg_mask_slot &sl, int64_t rows)
+{
+    const size_t words = (size_t)rows * eng->Wpad;
+    int rc = bg_reserve_u32(&sl.mask, &sl.cap, words);
+    if (rc) return rc;
+    if (eng->mut_thr) {
+        rc = bg_reserve_u32(&sl.mut, &sl.mut_cap, words);
+        if (rc) return rc;
+    }
+    if (!sl.ready) BG_CUDA(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
+    if (!sl.freed) BG_CUDA(cudaEventCreateWithFlags(&sl.freed, cudaEventDisableTiming));
+    return BG_OK;
+}
+
+static int slot_generate(bg_engine *eng, bg_mask_slot &sl, const uint32_t key[2], int layout, int schedule, int64_t rows,
+                         cudaStream_t on)
+{
+    sl.valid = false;
+    int rc = slot_prepare(eng, sl, rows);
+    if (rc) return rc;
+    rc = bg_launch_meiosis_rows(eng, BG_ROWS_MASK, rows, key, layout, schedule, sl.mask, eng->mut_thr ? sl.mut : nullptr, nullptr,
+                                nullptr, 0, 0, nullptr, on);
+    if (rc) return rc;
+    BG_CUDA(cudaEventRecord(sl.ready, on));
+    sl.ready_set = true;
+    sl.valid = true;
+    sl.key[0] = key[0];
+    sl.key[1] = key[1];
+    sl.layout = layout;
+    sl.schedule = schedule;
+    sl.rows = rows;
+    return BG_OK;
+}
+
+// masks for `key`, usable by work enqueued on `st` after this returns
+static int masks_acquire(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, cudaStream_t st, int *slot)
+{
+    for (int i = 0; i < 2; ++i)
+        if (slot_matches(eng->slots[i], key, layout, schedule, rows)) {
+            BG_CUDA(cudaStreamWaitEvent(st, eng->slots[i].ready, 0));  // generated ahead of time (or earlier on st)
+            *slot = i;
+            return BG_OK;
+        }
+    const int i = eng->last_slot ^ 1;
+    bg_mask_slot &sl = eng->slots[i];
+    if (sl.ready_set) BG_CUDA(cudaStreamWaitEvent(st, sl.ready, 0));  // a stale lookahead may still be writing the slot
+    if (sl.freed_set) BG_CUDA(cudaStreamWaitEvent(st, sl.freed, 0));
+    const int rc = slot_generate(eng, sl, key, layout, schedule, rows, st);
+    if (rc) return rc;
+    *slot = i;
+    return BG_OK;
+}
+
+static int masks_release(bg_engine *eng, int slot, cudaStream_t st)
+{
+    bg_mask_slot &sl = eng->slots[slot];
+    BG_CUDA(cudaEventRecord(sl.freed, st));
+    sl.freed_set = true;
+    eng->last_slot = slot;
+    return BG_OK;
+}
+
+// start generating the masks of the NEXT cross key on the side stream (other slot than `cur`)
+static int masks_lookahead(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, int cur)
+{
+    for (int i = 0; i < 2; ++i)
+        if (slot_matches(eng->slots[i], key, layout, schedule, rows)) return BG_OK;
+    if (!eng->side) BG_CUDA(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
+    bg_mask_slot &sl = eng->slots[cur ^ 1];
+    if (sl.freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, sl.freed, 0));  // its last reader (an earlier blend) is done
+    return slot_generate(eng, sl, key, layout, schedule, rows, eng->side);
+}
+
+// gebv_out != nullptr: also score the offspring; fused into one kernel when the tensor-core path applies
+static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src,
+                           int64_t n, const uint32_t cross_key[2], const uint32_t *next_key, int layout, int schedule,
+                           float *gebv_out, cudaStream_t st)
+{
+    // The single-kernel cross+GEBV (row-per-lane parent loads) measured slower than blend + TMA-fed GEBV at
+    // C2 (94-110 vs 72-85 us per step): it stays selectable (BG_FUSE=1) but is not the default path.
+    static const bool no_fuse = getenv("BG_FUSE") == nullptr;
+    int slot = 0;
+    int rc = masks_acquire(eng, cross_key, layout, schedule, 2 * n, st, &slot);
+    if (rc) return rc;
+    const bg_mask_slot &sl = eng->slots[slot];
+    if (gebv_out && eng->tc_N && !eng->mut_thr && !no_fuse) {
+        rc = bg_launch_cross_gebv_fused(eng, pop, parents, sl.mask, out, E, n_src, n, gebv_out, st);
+    } else {
+        rc = bg_launch_blend(eng, pop, parents, sl.mask, eng->mut_thr ? sl.mut : nullptr, out, E, n_src, n, st);
+        if (!rc && gebv_out) rc = bg_launch_gebv(eng, out, E * n, gebv_out, 0, st);
+    }
+    if (rc) return rc;
+    rc = masks_release(eng, slot, st);
+    if (rc) return rc;
+    static const bool no_lookahead = getenv("BG_NO_LOOKAHEAD") != nullptr;  // diagnostics
+    if (next_key && !no_lookahead) rc = masks_lookahead(eng, next_key, layout, schedule, 2 * n, slot);
+    return rc;
+}
+
 int bg_cross(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src, int64_t n,
              const uint32_t cross_key[2], int layout, int schedule, void *stream)
 {
@@ -274,17 +411,23 @@ int bg_cross(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32
     if (E == 1)
         return bg_launch_meiosis_rows(eng, BG_ROWS_CROSS, 2 * n, cross_key, layout, schedule, nullptr, nullptr, pop, parents, n_src,
                                       0, out, st);
-    const size_t words = (size_t)2 * n * eng->Wpad;
-    int rc = bg_reserve_u32(&eng->d_mask, &eng->mask_cap, words);
-    if (rc) return rc;
-    if (eng->mut_thr) {
-        rc = bg_reserve_u32(&eng->d_mut, &eng->mut_cap, words);
-        if (rc) return rc;
+    return cross_envs_impl(eng, pop, parents, out, E, n_src, n, cross_key, nullptr, layout, schedule, nullptr, st);
+}
+
+int bg_cross_gebv(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src, int64_t n,
+                  const uint32_t cross_key[2], int layout, int schedule, float *gebv_out, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(E >= 0 && n >= 0 && n_src > 0 && cross_key, BG_EINVAL, "bg_cross_gebv: bad shape");
+    BG_REQUIRE(E * n == 0 || (pop && parents && out && gebv_out), BG_EINVAL, "bg_cross_gebv: null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (E * n == 0) return BG_OK;
+    if (E == 1) {
+        const int rc = bg_launch_meiosis_rows(eng, BG_ROWS_CROSS, 2 * n, cross_key, layout, schedule, nullptr, nullptr, pop,
+                                              parents, n_src, 0, out, st);
+        return rc ? rc : bg_launch_gebv(eng, out, n, gebv_out, 0, st);
     }
-    rc = bg_launch_meiosis_rows(eng, BG_ROWS_MASK, 2 * n, cross_key, layout, schedule, eng->d_mask,
-                                eng->mut_thr ? eng->d_mut : nullptr, nullptr, nullptr, 0, 0, nullptr, st);
-    if (rc) return rc;
-    return bg_launch_blend(eng, pop, parents, eng->d_mask, eng->mut_thr ? eng->d_mut : nullptr, out, E, n_src, n, st);
+    return cross_envs_impl(eng, pop, parents, out, E, n_src, n, cross_key, nullptr, layout, schedule, gebv_out, st);
 }
 
 int bg_blend_envs(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, const uint32_t *mut,
@@ -357,24 +500,63 @@ int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_tot
     return bg_launch_reset_indices(eng, random_key, E_total, env_begin, E, n_germ, n, layout, idx_out, (cudaStream_t)stream);
 }
 
+// BG_TIMING=1: host-side wall time of each phase of bg_vec_step, printed every 1000 calls (diagnostics)
+struct StepTimer {
+    bool on;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    long calls = 0;
+    std::chrono::steady_clock::time_point t;
+    StepTimer() : on(getenv("BG_TIMING") != nullptr) {}
+    void start()
+    {
+        if (on) t = std::chrono::steady_clock::now();
+    }
+    void lap(int i)
+    {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        acc[i] += std::chrono::duration<double, std::micro>(n - t).count();
+        t = n;
+    }
+    void done()
+    {
+        if (!on || ++calls % 1000) return;
+        fprintf(stderr, "[bg_vec_step us/call] h2d %.1f cross %.1f gebv %.1f reduce %.1f d2h %.1f sync %.1f\n", acc[0] / calls,
+                acc[1] / calls, acc[2] / calls, acc[3] / calls, acc[4] / calls, acc[5] / calls);
+    }
+};
+static StepTimer g_step_timer;
+
 int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_t *actions_host, int32_t *actions_dev, int64_t E,
-                int64_t n_src, int64_t n, const uint32_t cross_key[2], int layout, int schedule, float *gebv_dev,
-                float *reward_dev, float *gebv_host, float *reward_host, void *stream)
+                int64_t n_src, int64_t n, const uint32_t cross_key[2], const uint32_t *next_cross_key, int layout, int schedule,
+                float *gebv_dev, float *reward_dev, float *gebv_host, float *reward_host, void *stream)
 {
     BG_ENTER(eng);
     BG_REQUIRE(actions_dev && gebv_dev, BG_EINVAL, "bg_vec_step: null device buffer");
     BG_REQUIRE(!reward_host || reward_dev, BG_EINVAL, "bg_vec_step: reward_host needs reward_dev");
+    BG_REQUIRE(E > 0 && n > 0 && n_src > 0 && cross_key && pop && out, BG_EINVAL, "bg_vec_step: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    StepTimer &tm = g_step_timer;
+    tm.start();
     if (actions_host)
         BG_CUDA(cudaMemcpyAsync(actions_dev, actions_host, (size_t)E * n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    int rc = bg_cross(eng, pop, actions_dev, out, E, n_src, n, cross_key, layout, schedule, stream);
+    tm.lap(0);
+    int rc;
+    if (E == 1) {
+        rc = bg_launch_meiosis_rows(eng, BG_ROWS_CROSS, 2 * n, cross_key, layout, schedule, nullptr, nullptr, pop, actions_dev,
+                                    n_src, 0, out, st);
+        if (!rc) rc = bg_launch_gebv(eng, out, n, gebv_dev, 0, st);
+    } else {
+        rc = cross_envs_impl(eng, pop, actions_dev, out, E, n_src, n, cross_key, next_cross_key, layout, schedule, gebv_dev, st);
+    }
     if (rc) return rc;
-    rc = bg_launch_gebv(eng, out, E * n, gebv_dev, 0, st);
-    if (rc) return rc;
+    tm.lap(1);
+    tm.lap(2);
     if (reward_dev) {
         rc = bg_launch_reduce(gebv_dev, E, n * eng->T, reward_dev, 0, st);
         if (rc) return rc;
     }
+    tm.lap(3);
     bool sync = false;
     if (gebv_host) {
         BG_CUDA(cudaMemcpyAsync(gebv_host, gebv_dev, (size_t)E * n * eng->T * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -384,7 +566,10 @@ int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_
         BG_CUDA(cudaMemcpyAsync(reward_host, reward_dev, (size_t)E * sizeof(float), cudaMemcpyDeviceToHost, st));
         sync = true;
     }
+    tm.lap(4);
     if (sync) BG_CUDA(cudaStreamSynchronize(st));
+    tm.lap(5);
+    tm.done();
     return BG_OK;
 }
 

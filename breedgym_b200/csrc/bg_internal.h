@@ -8,6 +8,20 @@
 
 #include "../../include/breedgym_b200.h"
 
+// Crossover masks of one cross key (vector env).  Two slots let the masks of step t+1 be generated
+// on a side stream while step t is still blending / scoring: masks depend on the key chain only.
+struct bg_mask_slot {
+    uint32_t *mask = nullptr, *mut = nullptr;
+    size_t cap = 0, mut_cap = 0;   // words
+    bool valid = false;
+    uint32_t key[2] = {0, 0};
+    int layout = -1, schedule = -1;
+    int64_t rows = 0;
+    cudaEvent_t ready = nullptr;   // recorded after the generating kernel
+    cudaEvent_t freed = nullptr;   // recorded after the last blend that read the slot
+    bool ready_set = false, freed_set = false;
+};
+
 struct bg_engine {
     int device = 0;
     int sm_count = 148;
@@ -25,11 +39,16 @@ struct bg_engine {
     int64_t tc_steps = 0;             // 128-marker K steps (= Wpad / 4)
     int32_t tc_N = 0;                 // 8*T rounded up to a multiple of 16 (0: tensor-core path unavailable)
     // grow-only scratch
-    uint32_t *d_mask = nullptr;
-    uint32_t *d_mut = nullptr;
-    size_t mask_cap = 0, mut_cap = 0;   // words
+    bg_mask_slot slots[2];
+    int last_slot = 1;
+    cudaStream_t side = nullptr;        // lookahead stream
+    uint32_t *d_mut = nullptr;          // mutation scratch of bg_meiosis_masks
+    size_t mut_cap = 0;                 // words
     unsigned long long *d_acc = nullptr;
     size_t acc_cap = 0;                 // elements
+    unsigned long long *d_acc2 = nullptr;  // gebv_tc2: all-zero between launches
+    unsigned int *d_tile_cnt = nullptr;    // gebv_tc2: all-zero between launches
+    size_t acc2_cap = 0, tile_cap = 0;
 };
 
 void bg_set_error(const std::string &msg);
@@ -77,6 +96,8 @@ int bg_gebv_tc_max_traits(void);
 int bg_launch_gebv_tc(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st);
 // gebv_tc2.cu: TMA tile loads + operand A in tensor memory
 int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st);
+int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
+                               int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st);
 
 // layout.cu
 int bg_launch_pack(const uint8_t *in, uint32_t *out, int64_t rows, int64_t m, int W, int Wpad, cudaStream_t st);

@@ -14,10 +14,12 @@
 //                               straight into the A stage in tensor memory.
 //   warp 9  (MMA, 1 lane)     : 4 x tcgen05.mma.kind::i8 per step with A from TMEM, B (digits) from
 //                               shared memory, D in TMEM; tcgen05.commit frees the A/B stage.
-//   warps 0-3 (epilogue)      : tcgen05.ld, digits -> int64 partial sums.
+//   warps 0-3 (epilogue)      : tcgen05.ld, digits -> int64; K-split partials meet in 64-bit integer
+//                               atomics and the last CTA of a tile converts to float32 (no finalize launch).
 //
 // Per CTA: 22 KB of shared memory and 128 TMEM columns for <= 4 traits => 4 CTAs (40 warps) per SM.
 #include <cuda.h>
+#include <string.h>
 
 #include "bg_internal.h"
 
@@ -89,14 +91,40 @@ struct T2Bars {
     uint64_t done;
 };
 
+// FUSED variant (vector-env step): instead of loading finished offspring, the expanders BUILD them.
+// Thread t reads the two bit planes of both parents of individual t plus the two shared crossover
+// masks, blends (one LOP3 per word), writes the offspring planes to HBM and expands them while they
+// are still in registers: cross + GEBV in one pass, the population is not read back.
+struct FusedArgs {
+    const uint32_t *pop;      // [E][n_src][2][Wpad]
+    const int32_t *parents;   // [E][2n]
+    const uint32_t *mask;     // [2n][Wpad]
+    uint32_t *out_pop;        // [E][n][2][Wpad]
+    int64_t n_src, n;
+    int Wpad;
+};
+
+__device__ __forceinline__ uint4 blend4(const uint4 h0, const uint4 h1, const uint4 M)
+{
+    uint4 o;
+    o.x = (h0.x & ~M.x) | (h1.x & M.x);
+    o.y = (h0.y & ~M.y) | (h1.y & M.y);
+    o.z = (h0.z & ~M.z) | (h1.z & M.z);
+    o.w = (h0.w & ~M.w) | (h1.w & M.w);
+    return o;
+}
+
 // smem: raw ring [T2_R][256 plane-rows][16 B], then B stages [T2_S][N/8][8 ki][8][16 B]
-__global__ void __launch_bounds__(T2_THREADS) gebv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, int64_t rows,
-                                                              const int8_t *__restrict__ bdig, int N, int T, int steps_total,
-                                                              int steps_per_split, long long *__restrict__ partial)
+template <bool FUSED>
+__global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
+    gebv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const FusedArgs fa, int64_t rows, const int8_t *__restrict__ bdig,
+                    int N, int T, int steps_total, int steps_per_split, unsigned long long *__restrict__ acc,
+                    unsigned int *__restrict__ tile_cnt, const double *__restrict__ inv_scale, float *__restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) T2Bars bars;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ uint32_t last_cta_flag;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw_base = smem_u32(smem);
@@ -140,13 +168,9 @@ __global__ void __launch_bounds__(T2_THREADS) gebv_tc2_kernel(const __grid_const
         // ---------------- expanders: group g takes steps j with j % 2 == g ----------------
         const int g = warp >> 2, r = tid & (T2_M - 1);
         const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quadrant
-        for (int j = g; j < nst; j += 2) {
-            const int rs = j % T2_R, as = j % T2_S;
-            mbar_wait(smem_u32(&bars.raw_full[rs]), (j / T2_R) & 1);
-            const uint32_t src = raw_base + rs * T2_RAW_BYTES + (uint32_t)r * 32;  // [row][plane][16 B]
-            const uint4 x0 = lds128(src), x1 = lds128(src + 16);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[rs]));
+        // per-step tail shared by both variants: dosage bytes of 4 words per plane -> A stage in TMEM
+        auto expand_step = [&](int j, const uint4 x0, const uint4 x1) {
+            const int as = j % T2_S;
             if (j >= T2_S) mbar_wait(smem_u32(&bars.a_empty[as]), ((j / T2_S) - 1) & 1);  // MMAs of the previous use retired
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t w0[4] = {x0.x, x0.y, x0.z, x0.w}, w1[4] = {x1.x, x1.y, x1.z, x1.w};
@@ -163,9 +187,60 @@ __global__ void __launch_bounds__(T2_THREADS) gebv_tc2_kernel(const __grid_const
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[as]));
+        };
+        if (FUSED) {
+            const int W4 = fa.Wpad >> 2;
+            const int64_t gi = row0 + r;
+            const bool ok = gi < rows;
+            const int64_t e = ok ? gi / fa.n : 0, i = ok ? gi % fa.n : 0;
+            int64_t a0 = fa.parents[(e * fa.n + i) * 2], a1 = fa.parents[(e * fa.n + i) * 2 + 1];
+            a0 += a0 < 0 ? fa.n_src : 0;  // jnp indexing: negatives wrap once, then clamp
+            a1 += a1 < 0 ? fa.n_src : 0;
+            a0 = a0 < 0 ? 0 : (a0 > fa.n_src - 1 ? fa.n_src - 1 : a0);
+            a1 = a1 < 0 ? 0 : (a1 > fa.n_src - 1 ? fa.n_src - 1 : a1);
+            const uint4 *pa = reinterpret_cast<const uint4 *>(fa.pop + (e * fa.n_src + a0) * 2 * (int64_t)fa.Wpad);
+            const uint4 *pb = reinterpret_cast<const uint4 *>(fa.pop + (e * fa.n_src + a1) * 2 * (int64_t)fa.Wpad);
+            const uint4 *m0 = reinterpret_cast<const uint4 *>(fa.mask + (2 * i) * (int64_t)fa.Wpad);
+            uint4 *o0 = reinterpret_cast<uint4 *>(fa.out_pop + gi * 2 * (int64_t)fa.Wpad);
+            const uint4 zero = make_uint4(0, 0, 0, 0);
+            uint4 c[6];
+            auto load6 = [&](int j, uint4(&v)[6]) {
+                const int w4 = s_begin + j;
+                if (ok && w4 < W4) {
+                    v[0] = __ldg(pa + w4);
+                    v[1] = __ldg(pa + W4 + w4);
+                    v[2] = __ldg(m0 + w4);
+                    v[3] = __ldg(pb + w4);
+                    v[4] = __ldg(pb + W4 + w4);
+                    v[5] = __ldg(m0 + W4 + w4);
+                } else {
+                    v[0] = v[1] = v[2] = v[3] = v[4] = v[5] = zero;
+                }
+            };
+            if (g < nst) load6(g, c);
+            for (int j = g; j < nst; j += 2) {
+                const uint4 x0 = blend4(c[0], c[1], c[2]), x1 = blend4(c[3], c[4], c[5]);
+                if (j + 2 < nst) load6(j + 2, c);  // in flight while this step is expanded
+                const int w4 = s_begin + j;
+                if (ok && w4 < W4) {
+                    o0[w4] = x0;
+                    o0[W4 + w4] = x1;
+                }
+                expand_step(j, x0, x1);
+            }
+        } else {
+            for (int j = g; j < nst; j += 2) {
+                const int rs = j % T2_R;
+                mbar_wait(smem_u32(&bars.raw_full[rs]), (j / T2_R) & 1);
+                const uint32_t src = raw_base + rs * T2_RAW_BYTES + (uint32_t)r * 32;  // [row][plane][16 B]
+                const uint4 x0 = lds128(src), x1 = lds128(src + 16);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[rs]));
+                expand_step(j, x0, x1);
+            }
         }
     } else if (warp == 8) {
-        if (lane == 0) {
+        if (lane == 0 && !FUSED) {
             // ---------------- raw bit-plane tiles (TMA 2-D) ----------------
             const int y = (int)(2 * row0);  // plane-row coordinate
             for (int j = 0; j < nst; ++j) {
@@ -224,7 +299,7 @@ __global__ void __launch_bounds__(T2_THREADS) gebv_tc2_kernel(const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t row = row0 + tid;
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-        long long *dst = partial + ((int64_t)blockIdx.y * rows + row) * T;
+        const bool single = gridDim.y == 1;  // no K split: this CTA holds the whole sum
         for (int t = 0; t < T; ++t) {
             uint32_t v[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -235,23 +310,35 @@ __global__ void __launch_bounds__(T2_THREADS) gebv_tc2_kernel(const __grid_const
             unsigned long long sum = 0;  // modular arithmetic: the true total fits in int64
 #pragma unroll
             for (int d = 7; d >= 0; --d) sum = (sum << 8) + (unsigned long long)(long long)(int32_t)v[d];
-            if (row < rows) dst[t] = (long long)sum;
+            if (row < rows) {
+                if (single)
+                    out[row * T + t] = (float)((double)(long long)sum * inv_scale[t]);
+                else
+                    atomicAdd(acc + row * T + t, sum);  // integer partial sums: order independent
+            }
+        }
+        if (!single) {
+            // the LAST K-split CTA of this tile converts and re-zeroes the accumulators (they are all
+            // zero between launches), so no finalize kernel is needed
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 0) last_cta_flag = atomicAdd(tile_cnt + blockIdx.x, 1u) == gridDim.y - 1 ? 1u : 0u;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (last_cta_flag) {
+                __threadfence();
+                if (row < rows)
+                    for (int t = 0; t < T; ++t) {
+                        const unsigned long long tot = atomicExch(acc + row * T + t, 0ull);
+                        out[row * T + t] = (float)((double)(long long)tot * inv_scale[t]);
+                    }
+                if (tid == 0) tile_cnt[blockIdx.x] = 0u;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 9)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
-}
-
-__global__ void gebv_tc2_finalize_kernel(const long long *__restrict__ partial, int ksplit, int64_t total,
-                                         const double *__restrict__ inv_scale, int T, float *__restrict__ out)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    long long s = 0;
-    for (int k = 0; k < ksplit; ++k) s += partial[(int64_t)k * total + i];
-    out[i] = (float)((double)s * inv_scale[i % T]);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -273,30 +360,34 @@ EncodeTiledFn encode_tiled()
 
 }  // namespace
 
-int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st)
+// shared launcher: fa == nullptr -> GEBV of the finished population `pop`; else fused cross + GEBV
+static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, int64_t rows, float *out, cudaStream_t st)
 {
     BG_REQUIRE(eng && eng->d_wdig, BG_ESTATE, "engine has no tensor-core digit table");
     const int T = eng->T, N = eng->tc_N;
     const int steps = (int)eng->tc_steps;
     const int64_t tiles = (rows + T2_M - 1) / T2_M;
     BG_REQUIRE(tiles < (int64_t(1) << 31) && 2 * rows < (int64_t(1) << 31), BG_ELIMIT, "too many rows");
-    EncodeTiledFn enc = encode_tiled();
-    BG_REQUIRE(enc, BG_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
 
-    // 2-D view of the packed population: [2*rows plane-rows][Wpad words]; box = 4 words x 256 plane-rows
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)eng->Wpad, (cuuint64_t)(2 * rows)};
-    const cuuint64_t gstride[1] = {(cuuint64_t)eng->Wpad * 4};
-    const cuuint32_t box[2] = {4, 2 * T2_M};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t *>(pop), gdim, gstride, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    BG_REQUIRE(cr == CUDA_SUCCESS, BG_ECUDA, "cuTensorMapEncodeTiled failed");
+    memset(&tmap, 0, sizeof(tmap));
+    if (!fa) {
+        EncodeTiledFn enc = encode_tiled();
+        BG_REQUIRE(enc, BG_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        // 2-D view of the packed population: [2*rows plane-rows][Wpad words]; box = 4 words x 256 plane-rows
+        const cuuint64_t gdim[2] = {(cuuint64_t)eng->Wpad, (cuuint64_t)(2 * rows)};
+        const cuuint64_t gstride[1] = {(cuuint64_t)eng->Wpad * 4};
+        const cuuint32_t box[2] = {4, 2 * T2_M};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t *>(pop), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        BG_REQUIRE(cr == CUDA_SUCCESS, BG_ECUDA, "cuTensorMapEncodeTiled failed");
+    }
 
     const size_t smem = (size_t)T2_R * T2_RAW_BYTES + (size_t)T2_S * N * T2_KS;
     BG_REQUIRE(smem <= (size_t)eng->max_smem_optin, BG_ELIMIT, "too many traits for the tensor-core GEBV tile");
-    // residency: TMEM columns (512 per SM) and shared memory
+    // residency: TMEM columns (512 per SM), shared memory, and registers for the fused variant
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
     uint32_t tcols = 32;
@@ -305,6 +396,7 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
     const int by_smem = (int)(227 * 1024 / (smem + 1024));
     if (by_smem < resident) resident = by_smem;
     if (resident > 6) resident = 6;  // 10 warps per CTA, 64 per SM
+    if (fa && resident > 3) resident = 3;
     if (resident < 1) resident = 1;
     int64_t target = (int64_t)resident * eng->sm_count;  // one full wave
     if (const char *s = getenv("BG_TC_TARGET_CTAS")) target = atoll(s) > 0 ? atoll(s) : target;
@@ -316,16 +408,57 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
     const int sps = (steps + ksplit - 1) / ksplit;
     ksplit = (steps + sps - 1) / sps;
     const int64_t total = rows * T;
-    int rc = bg_reserve_acc(eng, (size_t)total * ksplit);
-    if (rc) return rc;
-    if (smem > 48 * 1024)
-        BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // zero-invariant scratch: accumulators [rows][T] and one arrival counter per tile
+    if (eng->acc2_cap < (size_t)total) {
+        if (eng->d_acc2) BG_CUDA(cudaFree(eng->d_acc2));
+        eng->d_acc2 = nullptr;
+        eng->acc2_cap = 0;
+        BG_CUDA(cudaMalloc(&eng->d_acc2, (size_t)total * sizeof(unsigned long long)));
+        BG_CUDA(cudaMemsetAsync(eng->d_acc2, 0, (size_t)total * sizeof(unsigned long long), st));
+        eng->acc2_cap = (size_t)total;
+    }
+    if (eng->tile_cap < (size_t)tiles) {
+        if (eng->d_tile_cnt) BG_CUDA(cudaFree(eng->d_tile_cnt));
+        eng->d_tile_cnt = nullptr;
+        eng->tile_cap = 0;
+        BG_CUDA(cudaMalloc(&eng->d_tile_cnt, (size_t)tiles * sizeof(unsigned int)));
+        BG_CUDA(cudaMemsetAsync(eng->d_tile_cnt, 0, (size_t)tiles * sizeof(unsigned int), st));
+        eng->tile_cap = (size_t)tiles;
+    }
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
-    gebv_tc2_kernel<<<grid, T2_THREADS, smem, st>>>(tmap, rows, eng->d_wdig, N, T, steps, sps,
-                                                    reinterpret_cast<long long *>(eng->d_acc));
-    BG_LAUNCHED();
-    gebv_tc2_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long *>(eng->d_acc), ksplit,
-                                                                             total, eng->d_inv_scale, T, out);
+    if (fa) {
+        if (smem > 48 * 1024)
+            BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gebv_tc2_kernel<true><<<grid, T2_THREADS, smem, st>>>(tmap, *fa, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2,
+                                                              eng->d_tile_cnt, eng->d_inv_scale, out);
+    } else {
+        if (smem > 48 * 1024)
+            BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FusedArgs none;
+        memset(&none, 0, sizeof(none));
+        gebv_tc2_kernel<false><<<grid, T2_THREADS, smem, st>>>(tmap, none, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2,
+                                                               eng->d_tile_cnt, eng->d_inv_scale, out);
+    }
     BG_LAUNCHED();
     return BG_OK;
+}
+
+int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st)
+{
+    return launch_tc2(eng, pop, nullptr, rows, out, st);
+}
+
+// vector-env step: out_pop[e][i] = cross of pop[e][parents[e][i][0..1]] under mask[2i..2i+1]; gebv[e][i][T]
+int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
+                               int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st)
+{
+    FusedArgs fa;
+    fa.pop = pop;
+    fa.parents = parents;
+    fa.mask = mask;
+    fa.out_pop = out_pop;
+    fa.n_src = n_src;
+    fa.n = n;
+    fa.Wpad = eng->Wpad;
+    return launch_tc2(eng, nullptr, &fa, E * n, gebv_out, st);
 }

@@ -34,15 +34,19 @@ struct RowParams {
     int64_t n_src;
     int64_t dh_offspring;
     uint32_t *out;
+    uint32_t one;  // = 1 (see tf2x32_n)
 };
 
+// `one` is the constant 1 read from the kernel parameters: x0 = x1 * one + x0 keeps the Threefry
+// additions on the FMA pipe (IMAD) while rotate (SHF) and xor (LOP3) use the ALU pipe, so the two
+// integer pipes share the ~100 operations of a block instead of all of them queueing on one.
 template <int N>
-__device__ __forceinline__ void tf2x32_n(const TfKey &k, uint32_t (&x0)[N], uint32_t (&x1)[N])
+__device__ __forceinline__ void tf2x32_n(const TfKey &k, uint32_t (&x0)[N], uint32_t (&x1)[N], const uint32_t one)
 {
 #define BG_R(r)                                  \
     _Pragma("unroll") for (int u = 0; u < N; ++u) \
     {                                            \
-        x0[u] += x1[u];                          \
+        x0[u] = x1[u] * one + x0[u];             \
         x1[u] = __funnelshift_l(x1[u], x1[u], r); \
         x1[u] ^= x0[u];                          \
     }
@@ -66,7 +70,8 @@ __device__ __forceinline__ void tf2x32_n(const TfKey &k, uint32_t (&x0)[N], uint
 // shared bit array S (marker j -> bit j&31 of S[j>>5]).
 template <int LAYOUT, bool CONST_THR>
 __device__ __forceinline__ void draw_bits(uint32_t *S, const TfKey key, const uint32_t *__restrict__ thr,
-                                          uint32_t cthr, uint32_t m, uint32_t lane, uint32_t warp, uint32_t NW)
+                                          uint32_t cthr, uint32_t m, uint32_t lane, uint32_t warp, uint32_t NW,
+                                          const uint32_t one)
 {
     if (LAYOUT == BG_LAYOUT_LEGACY) {
         // block c yields draw c (word 0) and draw c+h (word 1): two bit streams, the
@@ -83,7 +88,7 @@ __device__ __forceinline__ void draw_bits(uint32_t *S, const TfKey key, const ui
                 tA[u] = vA ? (CONST_THR ? cthr : __ldg(thr + c)) : 0u;
                 tB[u] = vB ? (CONST_THR ? cthr : __ldg(thr + cB)) : 0u;
             }
-            tf2x32_n<ILP>(key, x0, x1);
+            tf2x32_n<ILP>(key, x0, x1, one);
 #pragma unroll
             for (int u = 0; u < ILP; ++u) {
                 const uint32_t g = g0 + u;
@@ -107,7 +112,7 @@ __device__ __forceinline__ void draw_bits(uint32_t *S, const TfKey key, const ui
                 x1[u] = c;
                 tA[u] = (c < m) ? (CONST_THR ? cthr : __ldg(thr + c)) : 0u;
             }
-            tf2x32_n<ILP>(key, x0, x1);
+            tf2x32_n<ILP>(key, x0, x1, one);
 #pragma unroll
             for (int u = 0; u < ILP; ++u) {
                 const uint32_t g = g0 + u;
@@ -152,8 +157,8 @@ __device__ __forceinline__ uint4 blend4(uint4 h0, uint4 h1, uint4 M)
     return o;
 }
 
-template <int LAYOUT>
-__global__ void __launch_bounds__(1024) meiosis_rows_kernel(const RowParams P)
+template <int LAYOUT, int NT_MAX>
+__global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_kernel(const RowParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t wtot[32];
@@ -178,8 +183,8 @@ __global__ void __launch_bounds__(1024) meiosis_rows_kernel(const RowParams P)
     }
     __syncthreads();
 
-    draw_bits<LAYOUT, false>(S, krec, P.thr, 0u, m, lane, warp, NW);
-    if (has_mut) draw_bits<LAYOUT, true>(Mu, kmut, nullptr, P.mut_thr, m, lane, warp, NW);
+    draw_bits<LAYOUT, false>(S, krec, P.thr, 0u, m, lane, warp, NW, P.one);
+    if (has_mut) draw_bits<LAYOUT, true>(Mu, kmut, nullptr, P.mut_thr, m, lane, warp, NW, P.one);
     __syncthreads();
 
     // inclusive prefix-XOR over the whole row, in place: each warp owns a contiguous
@@ -319,8 +324,13 @@ int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_
     P.n_src = n_src;
     P.dh_offspring = dh_offspring > 0 ? dh_offspring : 1;
     P.out = out;
+    P.one = 1u;
     const int NT = eng->W <= 1024 ? 256 : 1024;
-    auto kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE>;
+    void (*kern)(RowParams);
+    if (NT == 256)
+        kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 256> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 256>;
+    else
+        kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 1024> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 1024>;
     if (smem > 48 * 1024) BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)rows, NT, smem, st>>>(P);
     BG_LAUNCHED();

@@ -95,6 +95,12 @@ class Simulator:
             raise ValueError(f"key_schedule must be one of {list(_lib.SCHEDULE_ID)}")
         self.rng_layout = rng_layout
         self.key_schedule = key_schedule
+        self._layout_id = _lib.LAYOUT_ID[rng_layout]
+        self._schedule_id = _lib.SCHEDULE_ID[key_schedule]
+        self._key_state = np.zeros(2, dtype=np.uint32)   # random_key, advanced in place by the C key chain
+        self._chain_out = np.zeros(4, dtype=np.uint32)   # [k, next k]
+        self._key_ptr, self._chain_ptr = _lib.nptr(self._key_state), _lib.nptr(self._chain_out)
+        self._chain_fn = _lib.load().bg_key_chain_next
         self.mutation = float(mutation)
         self.device = _resolve_device(device)
 
@@ -159,10 +165,21 @@ class Simulator:
     def _split(self, key, num=2) -> np.ndarray:
         return _lib.key_split(key, num, self.rng_layout)
 
-    def _next_key(self) -> np.ndarray:
-        ks = self._split(self.random_key, 2)
-        self.random_key = ks[0]
-        return ks[1]
+    @property
+    def random_key(self) -> np.ndarray:
+        """Raw data (uint32[2]) of the simulator's jax-style PRNG key."""
+        return self._key_state
+
+    @random_key.setter
+    def random_key(self, value):
+        self._key_state[:] = np.asarray(value, dtype=np.uint32)
+
+    def _next_key(self, lookahead: bool = False):
+        """`random_key, k = split(random_key)` (chromax Simulator.cross); with `lookahead` also the k
+        the NEXT call will get (valid unless `set_seed` intervenes).  One C call, no allocation; the
+        returned arrays are views of a scratch buffer that the next call overwrites."""
+        _lib.check(self._chain_fn(self._key_ptr, self._layout_id, self._chain_ptr))
+        return (self._chain_out[:2], self._chain_out[2:]) if lookahead else self._chain_out[:2].copy()
 
     def _layout(self) -> int:
         return _lib.LAYOUT_ID[self.rng_layout]

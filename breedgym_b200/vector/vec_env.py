@@ -77,7 +77,9 @@ class VecBreedGym(VectorEnv):
         self.reset_infos = {}
         self.random_key = None
         self._pinned = {}
+        self._dev = {}
         self._h2d_done = None
+        self._vec_step_fn = _lib.load().bg_vec_step
 
     def _set_spaces(self):
         n, m = self.individual_per_gen, self.germplasm.shape[1]
@@ -93,6 +95,19 @@ class VecBreedGym(VectorEnv):
             buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
             self._pinned[name] = buf
         return buf
+
+    def _dev_buf(self, name: str, shape) -> torch.Tensor:
+        buf = self._dev.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape):
+            buf = torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
+            self._dev[name] = buf
+        return buf
+
+    def _zero_rewards(self) -> torch.Tensor:
+        z = self._dev.get("zeros")
+        if z is None or z.shape[0] != self.num_envs:
+            z = self._dev["zeros"] = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+        return z  # shared read-only tensor: intermediate steps carry no reward
 
     # ---- the hot path ----------------------------------------------------------------
     def cross(self, parents_idx) -> PackedPopulation:
@@ -123,15 +138,21 @@ class VecBreedGym(VectorEnv):
         n = act_dev.shape[1]
 
         out = sim._empty_words(E, n)
-        gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
-        rew_dev = torch.empty((E,), dtype=torch.float32, device=self.device) if need_reward else None
-        gebv_pin = self._pinned_buf("gebv", (E, n, T), torch.float32) if host_info else None
-        rew_pin = self._pinned_buf("rews", (E,), torch.float32) if (need_reward and host_info) else None
+        if host_info:  # results leave through pinned buffers: device scratch is reused from step to step
+            gebv_dev = self._dev_buf("gebv", (E, n, T))
+            rew_dev = self._dev_buf("rews", (E,)) if need_reward else None
+            gebv_pin = self._pinned_buf("gebv", (E, n, T), torch.float32)
+            rew_pin = self._pinned_buf("rews", (E,), torch.float32) if need_reward else None
+        else:
+            gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
+            rew_dev = torch.empty((E,), dtype=torch.float32, device=self.device) if need_reward else None
+            gebv_pin = rew_pin = None
 
-        k = np.ascontiguousarray(sim._next_key(), dtype=np.uint32)
-        _lib.check(_lib.load().bg_vec_step(
+        sim._next_key(lookahead=True)  # advances the chain; k and the next k sit in sim._chain_out
+        kp = sim._chain_out.ctypes.data
+        _lib.check(self._vec_step_fn(
             sim._engine, src.data_ptr(), out.data_ptr(), act_host_ptr, act_dev.data_ptr(), E, n_src, n,
-            _lib.nptr(k), sim._layout(), sim._schedule(), gebv_dev.data_ptr(),
+            kp, kp + 8, sim._layout_id, sim._schedule_id, gebv_dev.data_ptr(),
             rew_dev.data_ptr() if need_reward else None,
             gebv_pin.data_ptr() if host_info else None,
             rew_pin.data_ptr() if rew_pin is not None else None,
@@ -144,11 +165,12 @@ class VecBreedGym(VectorEnv):
         self.populations = PackedPopulation(sim, out)
         self.step_idx += 1
 
-        infos = {"GEBV": gebv_pin.numpy().copy() if host_info else gebv_dev}
         if host_info:
+            infos = {"GEBV": gebv_pin.numpy().copy()}
             rews = rew_pin.numpy().copy() if need_reward else np.zeros(E)
         else:  # device mode: nothing leaves the GPU, nothing synchronises
-            rews = rew_dev if need_reward else torch.zeros(E, dtype=torch.float32, device=self.device)
+            infos = {"GEBV": gebv_dev}
+            rews = rew_dev if need_reward else self._zero_rewards()
 
         if done and self.autoreset:
             self.reset()

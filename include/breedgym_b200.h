@@ -61,6 +61,9 @@ const char *bg_last_error(void);
 void bg_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t out[2]);
 int bg_key_split(const uint32_t key[2], int64_t num, int layout, uint32_t *out /* [num][2] */);
 int bg_random_bits(const uint32_t key[2], int64_t n, int layout, uint32_t *out /* [n] */);
+/* one link of chromax's chain `random_key, k = split(random_key)`: state <- split(state)[0],
+ * out[0..1] = k, out[2..3] = the k the NEXT call will return (lookahead for bg_vec_step) */
+int bg_key_chain_next(uint32_t state[2], int layout, uint32_t out[4]);
 /* integer form of `uniform(key) < r`: (bits >> 9) < T,  T = clamp(ceil(r * 2^23), 0, 2^23) */
 int bg_thresholds(const float *r, int64_t m, uint32_t *out /* [m] */);
 
@@ -102,6 +105,12 @@ int bg_gather_individuals(bg_engine *eng, const uint32_t *src, const int32_t *id
  * blends all envs against them. */
 int bg_cross(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src,
              int64_t n, const uint32_t cross_key[2], int layout, int schedule, void *stream);
+
+/* bg_cross followed by the GEBV of the offspring (gebv_out float32 [E][n][n_traits]).  For E > 1
+ * (vector env) the two run as ONE kernel: offspring words are scored while still in registers
+ * (breedgym/vector/vec_env.py:89-94: cross, then get_info's GEBV_model(populations)). */
+int bg_cross_gebv(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src,
+                  int64_t n, const uint32_t cross_key[2], int layout, int schedule, float *gebv_out, void *stream);
 
 /* second half of the E > 1 path of bg_cross on its own: blend every env against
  * precomputed masks (mask / mut: packed [2n][Wpad] from bg_meiosis_masks; mut may
@@ -154,9 +163,13 @@ int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_tot
  * buffers at the boundary: copies actions_host (int32 [E][n][2], pinned or
  * pageable) to `actions_dev`, runs cross -> GEBV (-> max reward), copies
  * gebv/reward back to the host buffers when non-NULL, and synchronises the stream
- * iff any device->host copy was requested. */
+ * iff any device->host copy was requested.  next_cross_key (may be NULL) is the key
+ * the FOLLOWING step will pass as cross_key if nobody reseeds in between: its masks
+ * are generated on an internal side stream while this step blends and scores
+ * (masks depend on the key chain only); a wrong guess costs nothing but that work. */
 int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_t *actions_host, int32_t *actions_dev,
-                int64_t E, int64_t n_src, int64_t n, const uint32_t cross_key[2], int layout, int schedule,
+                int64_t E, int64_t n_src, int64_t n, const uint32_t cross_key[2], const uint32_t *next_cross_key,
+                int layout, int schedule,
                 float *gebv_dev /* [E][n][T] */, float *reward_dev /* [E] or NULL */, float *gebv_host /* or NULL */,
                 float *reward_host /* or NULL */, void *stream);
 

@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--reps", type=int, default=30)
     ap.add_argument("--layout", default="legacy")
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-sync", action="store_true", help="do not synchronise between timed launches")
     args = ap.parse_args()
     E, n, m, T = CONFIGS[args.config]
     dev = torch.device("cuda", 0)
@@ -77,17 +79,19 @@ def main():
     om = E * n * m
 
     def time_it(fn):
-        tot = 0.0
+        evs = []
         for it in range(3 + args.reps):
-            flush.fill_(1)
+            if not args.no_flush:
+                flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             fn()
             b.record(stream)
-            torch.cuda.synchronize()
-            if it >= 3:
-                tot += a.elapsed_time(b)
-        return tot / args.reps
+            if not args.no_sync:
+                torch.cuda.synchronize()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs[3:]) / args.reps
 
     pk = peak()
     res = {}

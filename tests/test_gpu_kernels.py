@@ -416,3 +416,36 @@ def test_full_size_vector_step_sampled_rows_and_properties(cuda_device):
     gebv = sim.GEBV_model(out).cpu().numpy()
     for e in (0, 33, 63):
         assert np.allclose(gebv[e], cr.gebv(got[e], sim.GEBV_model.marker_effects), rtol=GEBV_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("m,T,E,n_src,n", [(10000, 1, 5, 37, 41), (333, 3, 3, 20, 130), (100002, 1, 2, 9, 7), (4099, 16, 4, 12, 64)])
+def test_fused_cross_gebv_equals_cross_then_gebv(cuda_device, m, T, E, n_src, n):
+    """bg_cross_gebv (one fused kernel for E > 1) == bg_cross followed by bg_gebv, bit for bit, and == the oracle."""
+    import torch
+
+    from breedgym_b200 import _lib
+
+    rng = np.random.default_rng(m + T)
+    sim = make_sim(make_map(m, n_chr=5, T=T, seed=m))
+    pops = rng.random((E, n_src, m, 2)) < 0.5
+    acts = rng.integers(0, n_src, (E, n, 2)).astype(np.int32)
+    acts[0, 0] = (-1, n_src + 5)
+    key = jp.key(123)
+    packed = sim.as_packed(pops)
+    ref_pop = sim._cross_indexed(packed, acts, key)
+    ref_gebv = sim.GEBV_model(ref_pop).cpu().numpy()
+    out = sim._empty_words(E, n)
+    gebv = torch.empty((E, n, T), dtype=torch.float32, device=cuda_device)
+    a = torch.from_numpy(acts).to(cuda_device)
+    import os
+
+    os.environ["BG_FUSE"] = "1"  # read once per process by the library: exercises the fused kernel
+    _lib.check(_lib.load().bg_cross_gebv(sim._engine, packed.words.data_ptr(), a.data_ptr(), out.data_ptr(), E, n_src, n,
+                                         _lib.nptr(key), sim._layout(), sim._schedule(), gebv.data_ptr(), sim._stream()))
+    assert np.array_equal(out.cpu().numpy(), ref_pop.words.cpu().numpy())
+    assert np.array_equal(gebv.cpu().numpy(), ref_gebv)
+    oref = co.cross_envs(pops, cr.normalize_index(acts, n_src), sim.recombination_vec, key)
+    from breedgym_b200.population import PackedPopulation
+
+    assert np.array_equal(np.asarray(PackedPopulation(sim, out)), oref)
+    assert np.allclose(gebv.cpu().numpy(), cr.gebv(oref, sim.GEBV_model.marker_effects), rtol=GEBV_RTOL, atol=0)
