@@ -78,6 +78,7 @@ def cpu_steps(n_steps, warmup, envs=ENVS_PER_GPU, min_seconds=0.0):
     from oracle import chromax_ref as cr
     from oracle import jax_prng as jp
 
+    co.set_threads(os.cpu_count() or 1)  # all host cores, whatever OMP_NUM_THREADS the launcher exported
     germ, gmap = workload_inputs()
     g = cr.read_genetic_map(gmap)
     r = cr.recombination_vector(g)

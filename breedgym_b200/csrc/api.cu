@@ -381,7 +381,7 @@ static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *p
 {
     // The single-kernel cross+GEBV (row-per-lane parent loads) measured slower than blend + TMA-fed GEBV at
     // C2 (94-110 vs 72-85 us per step): it stays selectable (BG_FUSE=1) but is not the default path.
-    static const bool no_fuse = getenv("BG_FUSE") == nullptr;
+    const bool no_fuse = getenv("BG_FUSE") == nullptr;
     int slot = 0;
     int rc = masks_acquire(eng, cross_key, layout, schedule, 2 * n, st, &slot);
     if (rc) return rc;

@@ -4,7 +4,7 @@
 // replaces chromax TraitModel.__call__, breedgym/breedgym.py:233, vec_env.py:132-134), but the
 // 128 x K dosage operand never touches shared memory:
 //
-//   warp 8  (loader, 2 lanes) : lane 0 streams raw bit-plane tiles [256 plane-rows x 16 B] with
+//   warp 8  (loader, 2 lanes) : lane 0 streams raw bit-plane tiles [256 plane-rows x 64 B = 4 steps] with
 //                               cp.async.bulk.tensor.2d (a tensor map over the packed population),
 //                               lane 1 streams the digit tiles with 1-D bulk copies; both land on
 //                               mbarriers with expect_tx, nothing sits on a thread's scoreboard.
@@ -17,7 +17,7 @@
 //   warps 0-3 (epilogue)      : tcgen05.ld, digits -> int64; K-split partials meet in 64-bit integer
 //                               atomics and the last CTA of a tile converts to float32 (no finalize launch).
 //
-// Per CTA: 22 KB of shared memory and 128 TMEM columns for <= 4 traits => 4 CTAs (40 warps) per SM.
+// Per CTA: 54 KB of shared memory and 128 TMEM columns for <= 4 traits => 4 CTAs (40 warps) per SM.
 #include <cuda.h>
 #include <string.h>
 
@@ -28,9 +28,11 @@ namespace {
 constexpr int T2_M = 128;
 constexpr int T2_KS = 128;          // markers per step (4 words per plane, 32 TMEM columns of int8x4)
 constexpr int T2_S = 3;             // A (TMEM) / B (smem) stages
-constexpr int T2_R = 4;             // raw tile ring
+constexpr int T2_R = 4;             // raw macro-tile ring
+constexpr int T2_SPM = 1;           // steps per raw macro tile (4 = 64-byte TMA rows measured slower: 38 vs 34.6 us at C2)
 constexpr int T2_THREADS = 256 + 64;
-constexpr uint32_t T2_RAW_BYTES = 2 * T2_M * 16;  // 256 plane-rows x 16 B
+constexpr uint32_t T2_RAW_ROW = 16 * T2_SPM;                 // bytes per plane-row in a macro tile
+constexpr uint32_t T2_RAW_BYTES = 2 * T2_M * T2_RAW_ROW;     // 256 plane-rows x 64 B
 constexpr uint32_t T2_SPIN_LIMIT = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,7 +116,7 @@ __device__ __forceinline__ uint4 blend4(const uint4 h0, const uint4 h1, const ui
     return o;
 }
 
-// smem: raw ring [T2_R][256 plane-rows][16 B], then B stages [T2_S][N/8][8 ki][8][16 B]
+// smem: raw ring [T2_R][256 plane-rows][64 B], then B stages [T2_S][N/8][8 ki][8][16 B]
 template <bool FUSED>
 __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
     gebv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const FusedArgs fa, int64_t rows, const int8_t *__restrict__ bdig,
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
     if (tid == 0) {
         for (int i = 0; i < T2_R; ++i) {
             mbar_init(smem_u32(&bars.raw_full[i]), 1);   // expect_tx arrival of the loader
-            mbar_init(smem_u32(&bars.raw_empty[i]), 4);  // the 4 warps of the group that read the tile
+            mbar_init(smem_u32(&bars.raw_empty[i]), 4 * T2_SPM);  // 4 warps per step x the steps that read the tile
         }
         for (int i = 0; i < T2_S; ++i) {
             mbar_init(smem_u32(&bars.a_full[i]), 4);   // the 4 warps of the group that filled the stage
@@ -177,10 +179,14 @@ __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
             const uint32_t ta = tmem_a + lane_sel + (uint32_t)as * (T2_KS / 4);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
+                // dosages as 2-bit fields first (even / odd markers: field f of ze <-> marker 2f, of zo <-> 2f+1; a
+                // field holds 0..2, no carry), then one shift + mask lifts 4 fields into 4 bytes:
+                // column q, byte b <-> K index 4q + b <-> marker 8b + q of this word.  22 integer ops per 32 markers.
+                const uint32_t ze = (w0[jj] & 0x55555555u) + (w1[jj] & 0x55555555u);
+                const uint32_t zo = ((w0[jj] >> 1) & 0x55555555u) + ((w1[jj] >> 1) & 0x55555555u);
                 uint32_t o[8];
 #pragma unroll
-                for (int sft = 0; sft < 8; ++sft)  // column sft, byte b <-> K index 4*sft + b <-> marker 8b + sft of this word
-                    o[sft] = ((w0[jj] >> sft) & 0x01010101u) + ((w1[jj] >> sft) & 0x01010101u);
+                for (int q = 0; q < 8; ++q) o[q] = (((q & 1) ? zo : ze) >> (q & ~1)) & 0x03030303u;
                 tmem_st8(ta + 8 * jj, o);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -230,10 +236,11 @@ __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
             }
         } else {
             for (int j = g; j < nst; j += 2) {
-                const int rs = j % T2_R;
-                mbar_wait(smem_u32(&bars.raw_full[rs]), (j / T2_R) & 1);
-                const uint32_t src = raw_base + rs * T2_RAW_BYTES + (uint32_t)r * 32;  // [row][plane][16 B]
-                const uint4 x0 = lds128(src), x1 = lds128(src + 16);
+                const int mt = j / T2_SPM, rs = mt % T2_R;
+                mbar_wait(smem_u32(&bars.raw_full[rs]), (mt / T2_R) & 1);
+                // macro tile [row][plane][64 B]; this step's 16 B of each plane
+                const uint32_t src = raw_base + rs * T2_RAW_BYTES + (uint32_t)r * (2 * T2_RAW_ROW) + (uint32_t)(j % T2_SPM) * 16;
+                const uint4 x0 = lds128(src), x1 = lds128(src + T2_RAW_ROW);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[rs]));
                 expand_step(j, x0, x1);
@@ -243,15 +250,16 @@ __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
         if (lane == 0 && !FUSED) {
             // ---------------- raw bit-plane tiles (TMA 2-D) ----------------
             const int y = (int)(2 * row0);  // plane-row coordinate
-            for (int j = 0; j < nst; ++j) {
-                const int rs = j % T2_R;
-                if (j >= T2_R) mbar_wait(smem_u32(&bars.raw_empty[rs]), ((j / T2_R) - 1) & 1);
+            const int nmt = (nst + T2_SPM - 1) / T2_SPM;
+            for (int mt = 0; mt < nmt; ++mt) {
+                const int rs = mt % T2_R;
+                if (mt >= T2_R) mbar_wait(smem_u32(&bars.raw_empty[rs]), ((mt / T2_R) - 1) & 1);
                 const uint32_t full = smem_u32(&bars.raw_full[rs]);
-                mbar_arrive_expect_tx(full, T2_RAW_BYTES);
+                mbar_arrive_expect_tx(full, T2_RAW_BYTES);  // out-of-bounds parts of the box are zero-filled and counted
                 asm volatile(
                     "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                         raw_base + rs * T2_RAW_BYTES),
-                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((s_begin + j) * 4), "r"(y), "r"(full)
+                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((s_begin + mt * T2_SPM) * 4), "r"(y), "r"(full)
                     : "memory");
             }
         } else if (lane == 1) {
@@ -374,10 +382,10 @@ static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, 
     if (!fa) {
         EncodeTiledFn enc = encode_tiled();
         BG_REQUIRE(enc, BG_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-        // 2-D view of the packed population: [2*rows plane-rows][Wpad words]; box = 4 words x 256 plane-rows
+        // 2-D view of the packed population: [2*rows plane-rows][Wpad words]; box = 16 words x 256 plane-rows
         const cuuint64_t gdim[2] = {(cuuint64_t)eng->Wpad, (cuuint64_t)(2 * rows)};
         const cuuint64_t gstride[1] = {(cuuint64_t)eng->Wpad * 4};
-        const cuuint32_t box[2] = {4, 2 * T2_M};
+        const cuuint32_t box[2] = {4 * T2_SPM, 2 * T2_M};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t *>(pop), gdim, gstride, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -426,14 +434,19 @@ static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, 
         eng->tile_cap = (size_t)tiles;
     }
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
+    static size_t optin_fused = 48 * 1024, optin_plain = 48 * 1024;  // largest dynamic smem opted into so far
     if (fa) {
-        if (smem > 48 * 1024)
+        if (smem > optin_fused) {
             BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            optin_fused = smem;
+        }
         gebv_tc2_kernel<true><<<grid, T2_THREADS, smem, st>>>(tmap, *fa, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2,
                                                               eng->d_tile_cnt, eng->d_inv_scale, out);
     } else {
-        if (smem > 48 * 1024)
+        if (smem > optin_plain) {
             BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            optin_plain = smem;
+        }
         FusedArgs none;
         memset(&none, 0, sizeof(none));
         gebv_tc2_kernel<false><<<grid, T2_THREADS, smem, st>>>(tmap, none, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2,

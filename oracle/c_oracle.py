@@ -94,4 +94,5 @@ def gebv(pop, effects):
 
 
 def set_threads(n: int):
-    os.environ["OMP_NUM_THREADS"] = str(n)
+    """Use n OpenMP threads (torchrun exports OMP_NUM_THREADS=1, which would hide the host's cores)."""
+    load().orc_set_threads(ctypes.c_int(int(n)))

@@ -170,6 +170,15 @@ void orc_gebv(const uint8_t *pop, const float *effects, int64_t rows, int64_t m,
     }
 }
 
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -439,9 +439,10 @@ def test_fused_cross_gebv_equals_cross_then_gebv(cuda_device, m, T, E, n_src, n)
     a = torch.from_numpy(acts).to(cuda_device)
     import os
 
-    os.environ["BG_FUSE"] = "1"  # read once per process by the library: exercises the fused kernel
+    os.environ["BG_FUSE"] = "1"  # read by the library on every call: exercises the single-kernel path
     _lib.check(_lib.load().bg_cross_gebv(sim._engine, packed.words.data_ptr(), a.data_ptr(), out.data_ptr(), E, n_src, n,
                                          _lib.nptr(key), sim._layout(), sim._schedule(), gebv.data_ptr(), sim._stream()))
+    os.environ.pop("BG_FUSE")
     assert np.array_equal(out.cpu().numpy(), ref_pop.words.cpu().numpy())
     assert np.array_equal(gebv.cpu().numpy(), ref_gebv)
     oref = co.cross_envs(pops, cr.normalize_index(acts, n_src), sim.recombination_vec, key)
