@@ -11,7 +11,10 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "libbreedgym_b200.so"
+import os
+
+# BG_LIB_PATH: load an experimental build of the same C ABI instead (kernel tuning only)
+LIB_PATH = Path(os.environ.get("BG_LIB_PATH") or Path(__file__).resolve().parent / "libbreedgym_b200.so")
 
 LAYOUT_ID = {"legacy": 0, "partitionable": 1}
 SCHEDULE_ID = {"S1": 1, "S2": 2}

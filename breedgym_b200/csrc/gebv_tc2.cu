@@ -27,7 +27,10 @@ namespace {
 
 constexpr int T2_M = 128;
 constexpr int T2_KS = 128;          // markers per step (4 words per plane, 32 TMEM columns of int8x4)
-constexpr int T2_S = 3;             // A (TMEM) / B (smem) stages
+#ifndef T2_S_VAL
+#define T2_S_VAL 3
+#endif
+constexpr int T2_S = T2_S_VAL;      // A (TMEM) / B (smem) stages
 constexpr int T2_R = 4;             // raw macro-tile ring
 constexpr int T2_SPM = 1;           // steps per raw macro tile (4 = 64-byte TMA rows measured slower: 38 vs 34.6 us at C2)
 constexpr int T2_THREADS = 256 + 64;

@@ -450,3 +450,59 @@ def test_fused_cross_gebv_equals_cross_then_gebv(cuda_device, m, T, E, n_src, n)
 
     assert np.array_equal(np.asarray(PackedPopulation(sim, out)), oref)
     assert np.allclose(gebv.cpu().numpy(), cr.gebv(oref, sim.GEBV_model.marker_effects), rtol=GEBV_RTOL, atol=0)
+
+
+def test_wheat_scale_c3_cross_and_gebv_sampled_rows(cuda_device):
+    """BASELINE config C3 (time_wheat.py shape): 1000 individuals x 100 002 markers x 21 chromosomes, one trait.
+    Unique-key cross at full size; sampled gamete rows and GEBV rows against the oracle."""
+    rng = np.random.default_rng(3)
+    m, n = 100_002, 1000
+    df = pd.DataFrame({"CHR.PHYS": np.arange(m) // 4762, "RecombRate": np.full(m, 1.5e-3),
+                       "Yield": rng.standard_normal(m).astype(np.float32)})
+    sim = make_sim(df)
+    assert len(sim.chr_lens) == 21
+    pop = rng.random((n, m, 2)) < 0.5
+    pairs = rng.integers(0, n, (n, 2))
+    key = jp.key(7)
+    out = sim._cross_indexed(sim.as_packed(pop), pairs, key)
+    got = np.asarray(out)
+    keys = jp.split(key, 2 * n)
+    for i, p in [(0, 0), (0, 1), (499, 1), (999, 0), (999, 1)]:
+        assert np.array_equal(got[i, :, p], cr.meiosis(pop[pairs[i, p]], sim.recombination_vec, keys[2 * i + p]))
+    gebv = sim.GEBV_model(out).cpu().numpy()
+    rows = [0, 1, 500, 999]
+    assert np.allclose(gebv[rows], cr.gebv(got[rows], sim.GEBV_model.marker_effects), rtol=GEBV_RTOL, atol=0)
+    # roughly 1.5e-3 * m + chromosome starts crossovers per gamete
+    switches = []
+    for i in range(20):  # where the parent's haplotypes differ the gamete reveals its source; count the switches
+        par = pop[pairs[i, 0]]
+        informative = par[:, 0] != par[:, 1]
+        src = (got[i, :, 0] == par[:, 1])[informative]
+        switches.append(np.count_nonzero(src[1:] != src[:-1]))
+    assert 80 < np.mean(switches) < 250  # expectation: 1.5e-3 * m + 21 chromosome starts / 2 ~ 160
+
+
+def test_million_marker_multi_trait_c4_shape(cuda_device):
+    """BASELINE config C4 row shape: 1 M markers, 16 traits (tensor-core GEBV), a reduced number of offspring
+    (the kernels are row-parallel: every gamete row is an independent function of (key, row))."""
+    import torch
+
+    rng = np.random.default_rng(4)
+    m, n_par, n_off, T = 1_000_000, 6, 24, 16
+    df = pd.DataFrame({"CHR.PHYS": np.arange(m) // 100_000, "RecombRate": np.full(m, 1.5e-3)})
+    for t in range(T):
+        df[f"t{t}"] = rng.standard_normal(m).astype(np.float32)
+    sim = make_sim(df)
+    pop = rng.random((n_par, m, 2)) < 0.5
+    pairs = rng.integers(0, n_par, (n_off, 2))
+    key = jp.key(11)
+    out = sim._cross_indexed(sim.as_packed(pop), pairs, key)
+    got = np.asarray(out)
+    keys = jp.split(key, 2 * n_off)
+    for i, p in [(0, 0), (23, 1), (11, 0)]:
+        assert np.array_equal(got[i, :, p], cr.meiosis(pop[pairs[i, p]], sim.recombination_vec, keys[2 * i + p]))
+    gebv = sim.GEBV_model(out).cpu().numpy()
+    assert gebv.shape == (n_off, T)
+    assert np.allclose(gebv, cr.gebv(got, sim.GEBV_model.marker_effects), rtol=GEBV_RTOL, atol=0)
+    assert np.array_equal(gebv, gebv_algo(sim, out, 4))  # both tensor-core variants agree bit for bit
+    torch.cuda.synchronize()
