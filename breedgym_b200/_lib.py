@@ -29,6 +29,7 @@ _SIGNATURES = {
     "bg_blend_envs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "bg_threefry2x32": (None, [c_uint32, c_uint32, c_uint32, c_uint32, c_void_p]),
     "bg_key_split": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
+    "bg_key_split_at": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "bg_random_bits": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
     "bg_key_chain_next": (c_int, [c_void_p, c_int, c_void_p]),
     "bg_thresholds": (c_int, [c_void_p, c_int64, c_void_p]),
@@ -96,6 +97,13 @@ def key_split(key: np.ndarray, num: int = 2, layout: str = "legacy") -> np.ndarr
     key = np.ascontiguousarray(key, dtype=np.uint32)
     out = np.empty((int(num), 2), dtype=np.uint32)
     check(load().bg_key_split(nptr(key), int(num), LAYOUT_ID[layout], nptr(out)))
+    return out
+
+
+def key_split_at(key: np.ndarray, index: int, num: int, layout: str = "legacy") -> np.ndarray:
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.empty(2, dtype=np.uint32)
+    check(load().bg_key_split_at(nptr(key), int(index), int(num), LAYOUT_ID[layout], nptr(out)))
     return out
 
 

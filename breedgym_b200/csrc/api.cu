@@ -105,6 +105,16 @@ int bg_key_chain_next(uint32_t state[2], int layout, uint32_t out[4])
     return BG_OK;
 }
 
+int bg_key_split_at(const uint32_t key[2], int64_t index, int64_t num, int layout, uint32_t out[2])
+{
+    BG_REQUIRE(key && out && num > 0 && index >= 0 && index < num, BG_EINVAL, "bg_key_split_at: bad argument");
+    BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
+    const TfKey s = tf_split_at(tf_make_key(key[0], key[1]), (uint64_t)index, (uint64_t)num, layout);
+    out[0] = s.k0;
+    out[1] = s.k1;
+    return BG_OK;
+}
+
 int bg_random_bits(const uint32_t key[2], int64_t n, int layout, uint32_t *out)
 {
     BG_REQUIRE(key && out && n >= 0, BG_EINVAL, "bg_random_bits: bad argument");

@@ -34,6 +34,9 @@ constexpr int T2_S = T2_S_VAL;      // A (TMEM) / B (smem) stages
 constexpr int T2_R = 4;             // raw macro-tile ring
 constexpr int T2_SPM = 1;           // steps per raw macro tile (4 = 64-byte TMA rows measured slower: 38 vs 34.6 us at C2)
 constexpr int T2_THREADS = 256 + 64;
+constexpr int T2F_THREADS = T2_THREADS + 128;   // fused: + 4 blender warps
+constexpr int T2F_MSTEPS = 8;                   // fused: steps per blended macro tile (128 B per plane-row)
+constexpr uint32_t T2F_TILE_BYTES = 2 * T2_M * 16 * T2F_MSTEPS;  // 128 rows x 2 planes x 128 B = 32 KB, 2 slots
 constexpr uint32_t T2_RAW_ROW = 16 * T2_SPM;                 // bytes per plane-row in a macro tile
 constexpr uint32_t T2_RAW_BYTES = 2 * T2_M * T2_RAW_ROW;     // 256 plane-rows x 64 B
 constexpr uint32_t T2_SPIN_LIMIT = 1u << 28;
@@ -96,10 +99,12 @@ struct T2Bars {
     uint64_t done;
 };
 
-// FUSED variant (vector-env step): instead of loading finished offspring, the expanders BUILD them.
-// Thread t reads the two bit planes of both parents of individual t plus the two shared crossover
-// masks, blends (one LOP3 per word), writes the offspring planes to HBM and expands them while they
-// are still in registers: cross + GEBV in one pass, the population is not read back.
+// FUSED variant (vector-env step): cross + GEBV in one pass, the offspring are never read back.
+// Four extra "blender" warps replace the TMA loader: 8 lanes cover 128 contiguous bytes of one parent
+// plane (fully coalesced 128-bit loads of both parent planes and the shared crossover mask), one LOP3
+// per word selects the alleles, the offspring words go to HBM (coalesced) and into a shared-memory
+// macro tile [128 rows][2 planes][8 x 16 B] whose 16-byte chunks are XOR-swizzled with the row so that
+// both the row-contiguous blender stores and the one-row-per-lane expander loads are bank-conflict free.
 struct FusedArgs {
     const uint32_t *pop;      // [E][n_src][2][Wpad]
     const int32_t *parents;   // [E][2n]
@@ -121,7 +126,7 @@ __device__ __forceinline__ uint4 blend4(const uint4 h0, const uint4 h1, const ui
 
 // smem: raw ring [T2_R][256 plane-rows][64 B], then B stages [T2_S][N/8][8 ki][8][16 B]
 template <bool FUSED>
-__global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
+__global__ void __launch_bounds__(FUSED ? T2F_THREADS : T2_THREADS, FUSED ? 3 : 4)
     gebv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const FusedArgs fa, int64_t rows, const int8_t *__restrict__ bdig,
                     int N, int T, int steps_total, int steps_per_split, unsigned long long *__restrict__ acc,
                     unsigned int *__restrict__ tile_cnt, const double *__restrict__ inv_scale, float *__restrict__ out)
@@ -130,11 +135,12 @@ __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
     __shared__ __align__(8) T2Bars bars;
     __shared__ uint32_t tmem_base_slot;
     __shared__ uint32_t last_cta_flag;
+    __shared__ uint32_t row_src[FUSED ? 2 * T2_M : 1], row_msk[FUSED ? 2 * T2_M : 1];  // per plane-row: uint4 offsets
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw_base = smem_u32(smem);
     const uint32_t b_bytes = (uint32_t)N * T2_KS;
-    const uint32_t b_base0 = raw_base + T2_R * T2_RAW_BYTES;
+    const uint32_t b_base0 = raw_base + (FUSED ? 2 * T2F_TILE_BYTES : T2_R * T2_RAW_BYTES);
     const int64_t row0 = (int64_t)blockIdx.x * T2_M;
     const int s_begin = blockIdx.y * steps_per_split;
     const int nst = min(steps_total, s_begin + steps_per_split) - s_begin;
@@ -152,8 +158,9 @@ __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
     }
     if (tid == 0) {
         for (int i = 0; i < T2_R; ++i) {
-            mbar_init(smem_u32(&bars.raw_full[i]), 1);   // expect_tx arrival of the loader
-            mbar_init(smem_u32(&bars.raw_empty[i]), 4 * T2_SPM);  // 4 warps per step x the steps that read the tile
+            // plain: expect_tx arrival of the TMA loader / 4 reader warps per step; fused: 4 blender warps / 8 steps x 4 warps
+            mbar_init(smem_u32(&bars.raw_full[i]), FUSED ? 4 : 1);
+            mbar_init(smem_u32(&bars.raw_empty[i]), FUSED ? 4 * T2F_MSTEPS : 4 * T2_SPM);
         }
         for (int i = 0; i < T2_S; ++i) {
             mbar_init(smem_u32(&bars.a_full[i]), 4);   // the 4 warps of the group that filled the stage
@@ -162,6 +169,24 @@ __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
         }
         mbar_init(smem_u32(&bars.done), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (FUSED) {
+        // plane-row (t, p) of the tile: source = plane 0 of parent p of individual t (plane 1 follows), mask row 2i+p
+        const int W4 = fa.Wpad >> 2;
+        for (int prow = tid; prow < 2 * T2_M; prow += blockDim.x) {
+            const int64_t gi = row0 + (prow >> 1);
+            uint32_t src = 0xFFFFFFFFu, msk = 0;
+            if (gi < rows) {
+                const int64_t e = gi / fa.n, i = gi % fa.n;
+                int64_t a = fa.parents[(e * fa.n + i) * 2 + (prow & 1)];
+                a += a < 0 ? fa.n_src : 0;  // jnp indexing: negatives wrap once, then clamp
+                a = a < 0 ? 0 : (a > fa.n_src - 1 ? fa.n_src - 1 : a);
+                src = (uint32_t)(((e * fa.n_src + a) * 2) * W4);
+                msk = (uint32_t)((2 * i + (prow & 1)) * W4);
+            }
+            row_src[prow] = src;
+            row_msk[prow] = msk;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -198,43 +223,14 @@ __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
             if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[as]));
         };
         if (FUSED) {
-            const int W4 = fa.Wpad >> 2;
-            const int64_t gi = row0 + r;
-            const bool ok = gi < rows;
-            const int64_t e = ok ? gi / fa.n : 0, i = ok ? gi % fa.n : 0;
-            int64_t a0 = fa.parents[(e * fa.n + i) * 2], a1 = fa.parents[(e * fa.n + i) * 2 + 1];
-            a0 += a0 < 0 ? fa.n_src : 0;  // jnp indexing: negatives wrap once, then clamp
-            a1 += a1 < 0 ? fa.n_src : 0;
-            a0 = a0 < 0 ? 0 : (a0 > fa.n_src - 1 ? fa.n_src - 1 : a0);
-            a1 = a1 < 0 ? 0 : (a1 > fa.n_src - 1 ? fa.n_src - 1 : a1);
-            const uint4 *pa = reinterpret_cast<const uint4 *>(fa.pop + (e * fa.n_src + a0) * 2 * (int64_t)fa.Wpad);
-            const uint4 *pb = reinterpret_cast<const uint4 *>(fa.pop + (e * fa.n_src + a1) * 2 * (int64_t)fa.Wpad);
-            const uint4 *m0 = reinterpret_cast<const uint4 *>(fa.mask + (2 * i) * (int64_t)fa.Wpad);
-            uint4 *o0 = reinterpret_cast<uint4 *>(fa.out_pop + gi * 2 * (int64_t)fa.Wpad);
-            const uint4 zero = make_uint4(0, 0, 0, 0);
-            uint4 c[6];
-            auto load6 = [&](int j, uint4(&v)[6]) {
-                const int w4 = s_begin + j;
-                if (ok && w4 < W4) {
-                    v[0] = __ldg(pa + w4);
-                    v[1] = __ldg(pa + W4 + w4);
-                    v[2] = __ldg(m0 + w4);
-                    v[3] = __ldg(pb + w4);
-                    v[4] = __ldg(pb + W4 + w4);
-                    v[5] = __ldg(m0 + W4 + w4);
-                } else {
-                    v[0] = v[1] = v[2] = v[3] = v[4] = v[5] = zero;
-                }
-            };
-            if (g < nst) load6(g, c);
             for (int j = g; j < nst; j += 2) {
-                const uint4 x0 = blend4(c[0], c[1], c[2]), x1 = blend4(c[3], c[4], c[5]);
-                if (j + 2 < nst) load6(j + 2, c);  // in flight while this step is expanded
-                const int w4 = s_begin + j;
-                if (ok && w4 < W4) {
-                    o0[w4] = x0;
-                    o0[W4 + w4] = x1;
-                }
+                const int mt = j / T2F_MSTEPS, slot = mt & 1;
+                mbar_wait(smem_u32(&bars.raw_full[slot]), (mt >> 1) & 1);
+                const uint32_t src = raw_base + slot * T2F_TILE_BYTES + (uint32_t)r * 256 +
+                                     (uint32_t)(((j % T2F_MSTEPS) ^ (r & 7)) * 16);  // swizzled 16-byte chunk of this step
+                const uint4 x0 = lds128(src), x1 = lds128(src + 128);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[slot]));
                 expand_step(j, x0, x1);
             }
         } else {
@@ -278,7 +274,37 @@ __global__ void __launch_bounds__(T2_THREADS, FUSED ? 3 : 4)
                              : "memory");
             }
         }
-    } else if (lane == 0) {
+    } else if (FUSED && warp >= 10) {
+        // ---------------- blenders: parents + masks -> offspring (HBM) + swizzled macro tile (smem) ----------------
+        const int W4 = fa.Wpad >> 2;
+        const uint4 *pop4 = reinterpret_cast<const uint4 *>(fa.pop);
+        const uint4 *mask4 = reinterpret_cast<const uint4 *>(fa.mask);
+        uint4 *out4 = reinterpret_cast<uint4 *>(fa.out_pop) + (int64_t)(2 * row0) * W4;
+        const int bw = warp - 10, c = lane & 7, rsub = lane >> 3;
+        const int nmt = (nst + T2F_MSTEPS - 1) / T2F_MSTEPS;
+        for (int mt = 0; mt < nmt; ++mt) {
+            const int slot = mt & 1;
+            if (mt >= 2) mbar_wait(smem_u32(&bars.raw_empty[slot]), ((mt >> 1) - 1) & 1);
+            const int w4 = s_begin + mt * T2F_MSTEPS + c;  // uint4 index inside the row = global step index
+            const uint32_t tile = raw_base + slot * T2F_TILE_BYTES;
+#pragma unroll 2
+            for (int pass = bw; pass < (2 * T2_M) / 4; pass += 4) {
+                const int prow = pass * 4 + rsub, t = prow >> 1;
+                const uint32_t src = row_src[prow];
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (src != 0xFFFFFFFFu && w4 < W4) {
+                    const uint4 h0 = __ldg(pop4 + src + w4), h1 = __ldg(pop4 + src + W4 + w4);
+                    const uint4 M = __ldg(mask4 + row_msk[prow] + w4);
+                    o = blend4(h0, h1, M);
+                    out4[(int64_t)prow * W4 + w4] = o;
+                }
+                const uint32_t dst = tile + (uint32_t)t * 256 + (uint32_t)(prow & 1) * 128 + (uint32_t)((c ^ (t & 7)) * 16);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars.raw_full[slot]));
+        }
+    } else if (warp == 9 && lane == 0) {
         // ---------------- MMA issuer ----------------
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(T2_M >> 4) << 24);
         for (int j = 0; j < nst; ++j) {
@@ -396,8 +422,12 @@ static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, 
         BG_REQUIRE(cr == CUDA_SUCCESS, BG_ECUDA, "cuTensorMapEncodeTiled failed");
     }
 
-    const size_t smem = (size_t)T2_R * T2_RAW_BYTES + (size_t)T2_S * N * T2_KS;
+    const size_t raw_bytes = fa ? (size_t)2 * T2F_TILE_BYTES : (size_t)T2_R * T2_RAW_BYTES;
+    const size_t smem = raw_bytes + (size_t)T2_S * N * T2_KS;
     BG_REQUIRE(smem <= (size_t)eng->max_smem_optin, BG_ELIMIT, "too many traits for the tensor-core GEBV tile");
+    if (fa)
+        BG_REQUIRE((int64_t)eng->Wpad / 4 * 2 * (fa->n_src > fa->n ? fa->n_src : fa->n) * ((rows + fa->n - 1) / fa->n) < (int64_t(1) << 32),
+                   BG_ELIMIT, "population too large for the fused kernel's 32-bit row offsets");
     // residency: TMEM columns (512 per SM), shared memory, and registers for the fused variant
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
@@ -443,7 +473,7 @@ static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, 
             BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             optin_fused = smem;
         }
-        gebv_tc2_kernel<true><<<grid, T2_THREADS, smem, st>>>(tmap, *fa, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2,
+        gebv_tc2_kernel<true><<<grid, T2F_THREADS, smem, st>>>(tmap, *fa, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2,
                                                               eng->d_tile_cnt, eng->d_inv_scale, out);
     } else {
         if (smem > optin_plain) {

@@ -78,6 +78,7 @@ class VecBreedGym(VectorEnv):
         self.random_key = None
         self._pinned = {}
         self._dev = {}
+        self._io = None
         self._h2d_done = None
         self._vec_step_fn = _lib.load().bg_vec_step
 
@@ -114,70 +115,102 @@ class VecBreedGym(VectorEnv):
         """Offspring of `populations[arange, parents_idx]`, one key for all envs (vec_env.py:75-77)."""
         return self.simulator.cross_envs(self.populations, parents_idx)
 
+    def _host_io(self, shape, T):
+        """Staging for the host-facing step, built once per action shape: pinned actions / GEBV / rewards
+        (with their numpy views and raw pointers) and the device scratch behind them."""
+        io = self._io
+        if io is None or io["shape"] != shape:
+            E, n = shape[0], shape[1]
+            dev = self.device
+            act_pin = torch.empty(shape, dtype=torch.int32, pin_memory=True)
+            gebv_pin = torch.empty((E, n, T), dtype=torch.float32, pin_memory=True)
+            rew_pin = torch.empty((E,), dtype=torch.float32, pin_memory=True)
+            act_dev = torch.empty(shape, dtype=torch.int32, device=dev)
+            gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=dev)
+            rew_dev = torch.empty((E,), dtype=torch.float32, device=dev)
+            io = self._io = {
+                "shape": shape, "keep": (act_pin, gebv_pin, rew_pin, act_dev, gebv_dev, rew_dev),
+                "act_np": act_pin.numpy(), "gebv_np": gebv_pin.numpy(), "rew_np": rew_pin.numpy(),
+                "act_pin": act_pin.data_ptr(), "gebv_pin": gebv_pin.data_ptr(), "rew_pin": rew_pin.data_ptr(),
+                "act_dev": act_dev.data_ptr(), "gebv_dev": gebv_dev.data_ptr(), "rew_dev": rew_dev.data_ptr(),
+            }
+        return io
+
     def step(self, actions):
         sim, E, T = self.simulator, self.num_envs, self.simulator.GEBV_model.n_traits
         done = self.step_idx + 1 == self.num_generations
         need_reward = self.reward_shaping or done
         host_info = self.info_device == "host"
-
         src = self.populations.words
         n_src = src.shape[1]
-        if isinstance(actions, torch.Tensor) and actions.is_cuda:
-            act_dev = actions.to(device=self.device, dtype=torch.int32).contiguous()
-            act_host_ptr = None
-        else:
+        on_device = isinstance(actions, torch.Tensor) and actions.is_cuda
+
+        if host_info and not on_device:
+            # ---- the Gym-facing path: numpy actions in, numpy GEBV / rewards out, one sync inside the C call
             a = np.asarray(actions)
-            act_pin = self._pinned_buf("actions", a.shape, torch.int32)
-            if self._h2d_done is not None:  # previous async H2D must have left the staging buffer
-                self._h2d_done.synchronize()
-            act_pin.numpy()[...] = a  # int64 -> int32 conversion happens in this copy
-            act_dev = torch.empty(a.shape, dtype=torch.int32, device=self.device)
-            act_host_ptr = act_pin.data_ptr()
-        if act_dev.dim() != 3 or act_dev.shape[0] != E or act_dev.shape[2] != 2:
-            raise ValueError(f"actions must have shape ({E}, n, 2), got {tuple(act_dev.shape)}")
-        n = act_dev.shape[1]
-
-        out = sim._empty_words(E, n)
-        if host_info:  # results leave through pinned buffers: device scratch is reused from step to step
-            gebv_dev = self._dev_buf("gebv", (E, n, T))
-            rew_dev = self._dev_buf("rews", (E,)) if need_reward else None
-            gebv_pin = self._pinned_buf("gebv", (E, n, T), torch.float32)
-            rew_pin = self._pinned_buf("rews", (E,), torch.float32) if need_reward else None
+            if a.ndim != 3 or a.shape[0] != E or a.shape[2] != 2:
+                raise ValueError(f"actions must have shape ({E}, n, 2), got {a.shape}")
+            n = a.shape[1]
+            io = self._host_io(a.shape, T)
+            io["act_np"][...] = a  # int64 -> int32 conversion happens in this copy
+            out = sim._empty_words(E, n)
+            sim._next_key(lookahead=True)  # advances the chain; k and the next k sit in sim._chain_out
+            kp = sim._chain_out.ctypes.data
+            _lib.check(self._vec_step_fn(
+                sim._engine, src.data_ptr(), out.data_ptr(), io["act_pin"], io["act_dev"], E, n_src, n, kp, kp + 8,
+                sim._layout_id, sim._schedule_id, io["gebv_dev"], io["rew_dev"] if need_reward else None,
+                io["gebv_pin"], io["rew_pin"] if need_reward else None, sim._stream()))
+            infos = {"GEBV": io["gebv_np"].copy()}
+            rews = io["rew_np"].copy() if need_reward else np.zeros(E)
         else:
-            gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
-            rew_dev = torch.empty((E,), dtype=torch.float32, device=self.device) if need_reward else None
-            gebv_pin = rew_pin = None
+            if on_device:
+                act_dev = actions.to(device=self.device, dtype=torch.int32).contiguous()
+                act_host_ptr = None
+            else:
+                a = np.asarray(actions)
+                act_pin = self._pinned_buf("actions", a.shape, torch.int32)
+                if self._h2d_done is not None:  # previous async H2D must have left the staging buffer
+                    self._h2d_done.synchronize()
+                act_pin.numpy()[...] = a
+                act_dev = torch.empty(a.shape, dtype=torch.int32, device=self.device)
+                act_host_ptr = act_pin.data_ptr()
+            if act_dev.dim() != 3 or act_dev.shape[0] != E or act_dev.shape[2] != 2:
+                raise ValueError(f"actions must have shape ({E}, n, 2), got {tuple(act_dev.shape)}")
+            n = act_dev.shape[1]
+            out = sim._empty_words(E, n)
+            if host_info:
+                gebv_dev = self._dev_buf("gebv", (E, n, T))
+                rew_dev = self._dev_buf("rews", (E,)) if need_reward else None
+                gebv_pin = self._pinned_buf("gebv", (E, n, T), torch.float32)
+                rew_pin = self._pinned_buf("rews", (E,), torch.float32) if need_reward else None
+            else:
+                gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
+                rew_dev = torch.empty((E,), dtype=torch.float32, device=self.device) if need_reward else None
+                gebv_pin = rew_pin = None
+            sim._next_key(lookahead=True)
+            kp = sim._chain_out.ctypes.data
+            _lib.check(self._vec_step_fn(
+                sim._engine, src.data_ptr(), out.data_ptr(), act_host_ptr, act_dev.data_ptr(), E, n_src, n, kp, kp + 8,
+                sim._layout_id, sim._schedule_id, gebv_dev.data_ptr(), rew_dev.data_ptr() if need_reward else None,
+                gebv_pin.data_ptr() if host_info else None, rew_pin.data_ptr() if rew_pin is not None else None,
+                sim._stream()))
+            if act_host_ptr is not None and not host_info:  # no sync happened inside the call
+                self._h2d_done = torch.cuda.Event()
+                self._h2d_done.record(torch.cuda.current_stream(self.device))
+            else:
+                self._h2d_done = None
+            if host_info:
+                infos = {"GEBV": gebv_pin.numpy().copy()}
+                rews = rew_pin.numpy().copy() if need_reward else np.zeros(E)
+            else:  # device mode: nothing leaves the GPU, nothing synchronises
+                infos = {"GEBV": gebv_dev}
+                rews = rew_dev if need_reward else self._zero_rewards()
 
-        sim._next_key(lookahead=True)  # advances the chain; k and the next k sit in sim._chain_out
-        kp = sim._chain_out.ctypes.data
-        _lib.check(self._vec_step_fn(
-            sim._engine, src.data_ptr(), out.data_ptr(), act_host_ptr, act_dev.data_ptr(), E, n_src, n,
-            kp, kp + 8, sim._layout_id, sim._schedule_id, gebv_dev.data_ptr(),
-            rew_dev.data_ptr() if need_reward else None,
-            gebv_pin.data_ptr() if host_info else None,
-            rew_pin.data_ptr() if rew_pin is not None else None,
-            sim._stream()))
-        if act_host_ptr is not None and not host_info:  # no sync happened inside the call
-            self._h2d_done = torch.cuda.Event()
-            self._h2d_done.record(torch.cuda.current_stream(self.device))
-        else:
-            self._h2d_done = None
         self.populations = PackedPopulation(sim, out)
         self.step_idx += 1
-
-        if host_info:
-            infos = {"GEBV": gebv_pin.numpy().copy()}
-            rews = rew_pin.numpy().copy() if need_reward else np.zeros(E)
-        else:  # device mode: nothing leaves the GPU, nothing synchronises
-            infos = {"GEBV": gebv_dev}
-            rews = rew_dev if need_reward else self._zero_rewards()
-
         if done and self.autoreset:
             self.reset()
-
-        terminated = np.full(E, False)
-        truncated = np.full(E, done)
-        return self.populations, rews, terminated, truncated, infos
+        return self.populations, rews, np.zeros(E, dtype=bool), np.full(E, done), infos
 
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
         self.step_idx = 0
@@ -200,7 +233,7 @@ class VecBreedGym(VectorEnv):
         # env g draws permutation(keys[1 + g], N)[:n] with keys = split(random_key, total + 1)
         _lib.check(lib.bg_reset_indices(sim._engine, _lib.nptr(key), total, begin, E, len(self.germplasm), n,
                                         sim._layout(), idx.data_ptr(), sim._stream()))
-        self.random_key = sim._split(self.random_key, total + 1)[0]
+        self.random_key = _lib.key_split_at(self.random_key, 0, total + 1, sim.rng_layout)
         words = sim._empty_words(E, n)
         germ = self.germplasm.words.contiguous()
         _lib.check(lib.bg_gather_individuals(sim._engine, germ.data_ptr(), idx.data_ptr(), words.data_ptr(), E,

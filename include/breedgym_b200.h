@@ -60,6 +60,8 @@ const char *bg_last_error(void);
  *  breedgym/vector/vec_env.py:115,120; breedgym/vector/vec_wrappers.py:82). */
 void bg_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t out[2]);
 int bg_key_split(const uint32_t key[2], int64_t num, int layout, uint32_t *out /* [num][2] */);
+/* element `index` of split(key, num) without computing the others (vec_env.py:120-121 keeps keys[0] only) */
+int bg_key_split_at(const uint32_t key[2], int64_t index, int64_t num, int layout, uint32_t out[2]);
 int bg_random_bits(const uint32_t key[2], int64_t n, int layout, uint32_t *out /* [n] */);
 /* one link of chromax's chain `random_key, k = split(random_key)`: state <- split(state)[0],
  * out[0..1] = k, out[2..3] = the k the NEXT call will return (lookahead for bg_vec_step) */
