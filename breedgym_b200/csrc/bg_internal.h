@@ -46,9 +46,11 @@ struct bg_engine {
     size_t mut_cap = 0;                 // words
     unsigned long long *d_acc = nullptr;
     size_t acc_cap = 0;                 // elements
-    unsigned long long *d_acc2 = nullptr;  // gebv_tc2: all-zero between launches
-    unsigned int *d_tile_cnt = nullptr;    // gebv_tc2: all-zero between launches
-    size_t acc2_cap = 0, tile_cap = 0;
+    unsigned long long *d_acc2[2] = {nullptr, nullptr};  // gebv_tc2: all-zero between launches (one set per stream)
+    unsigned int *d_tile_cnt[2] = {nullptr, nullptr};    // gebv_tc2: all-zero between launches
+    size_t acc2_cap[2] = {0, 0}, tile_cap[2] = {0, 0};
+    cudaStream_t side2 = nullptr;          // second half of a split step scores here while the first half still blends
+    cudaEvent_t ev_half = nullptr, ev_half_done = nullptr;
 };
 
 void bg_set_error(const std::string &msg);
@@ -95,7 +97,7 @@ int bg_launch_reduce(const float *in, int64_t E, int64_t per_env, float *out, in
 int bg_gebv_tc_max_traits(void);
 int bg_launch_gebv_tc(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st);
 // gebv_tc2.cu: TMA tile loads + operand A in tensor memory
-int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st);
+int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st, int scratch = 0);
 int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
                                int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st);
 

@@ -398,7 +398,8 @@ EncodeTiledFn encode_tiled()
 }  // namespace
 
 // shared launcher: fa == nullptr -> GEBV of the finished population `pop`; else fused cross + GEBV
-static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, int64_t rows, float *out, cudaStream_t st)
+static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, int64_t rows, float *out, cudaStream_t st,
+                      int scratch = 0)
 {
     BG_REQUIRE(eng && eng->d_wdig, BG_ESTATE, "engine has no tensor-core digit table");
     const int T = eng->T, N = eng->tc_N;
@@ -450,21 +451,21 @@ static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, 
     ksplit = (steps + sps - 1) / sps;
     const int64_t total = rows * T;
     // zero-invariant scratch: accumulators [rows][T] and one arrival counter per tile
-    if (eng->acc2_cap < (size_t)total) {
-        if (eng->d_acc2) BG_CUDA(cudaFree(eng->d_acc2));
-        eng->d_acc2 = nullptr;
-        eng->acc2_cap = 0;
-        BG_CUDA(cudaMalloc(&eng->d_acc2, (size_t)total * sizeof(unsigned long long)));
-        BG_CUDA(cudaMemsetAsync(eng->d_acc2, 0, (size_t)total * sizeof(unsigned long long), st));
-        eng->acc2_cap = (size_t)total;
+    if (eng->acc2_cap[scratch] < (size_t)total) {
+        if (eng->d_acc2[scratch]) BG_CUDA(cudaFree(eng->d_acc2[scratch]));
+        eng->d_acc2[scratch] = nullptr;
+        eng->acc2_cap[scratch] = 0;
+        BG_CUDA(cudaMalloc(&eng->d_acc2[scratch], (size_t)total * sizeof(unsigned long long)));
+        BG_CUDA(cudaMemsetAsync(eng->d_acc2[scratch], 0, (size_t)total * sizeof(unsigned long long), st));
+        eng->acc2_cap[scratch] = (size_t)total;
     }
-    if (eng->tile_cap < (size_t)tiles) {
-        if (eng->d_tile_cnt) BG_CUDA(cudaFree(eng->d_tile_cnt));
-        eng->d_tile_cnt = nullptr;
-        eng->tile_cap = 0;
-        BG_CUDA(cudaMalloc(&eng->d_tile_cnt, (size_t)tiles * sizeof(unsigned int)));
-        BG_CUDA(cudaMemsetAsync(eng->d_tile_cnt, 0, (size_t)tiles * sizeof(unsigned int), st));
-        eng->tile_cap = (size_t)tiles;
+    if (eng->tile_cap[scratch] < (size_t)tiles) {
+        if (eng->d_tile_cnt[scratch]) BG_CUDA(cudaFree(eng->d_tile_cnt[scratch]));
+        eng->d_tile_cnt[scratch] = nullptr;
+        eng->tile_cap[scratch] = 0;
+        BG_CUDA(cudaMalloc(&eng->d_tile_cnt[scratch], (size_t)tiles * sizeof(unsigned int)));
+        BG_CUDA(cudaMemsetAsync(eng->d_tile_cnt[scratch], 0, (size_t)tiles * sizeof(unsigned int), st));
+        eng->tile_cap[scratch] = (size_t)tiles;
     }
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
     static size_t optin_fused = 48 * 1024, optin_plain = 48 * 1024;  // largest dynamic smem opted into so far
@@ -473,8 +474,8 @@ static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, 
             BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             optin_fused = smem;
         }
-        gebv_tc2_kernel<true><<<grid, T2F_THREADS, smem, st>>>(tmap, *fa, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2,
-                                                              eng->d_tile_cnt, eng->d_inv_scale, out);
+        gebv_tc2_kernel<true><<<grid, T2F_THREADS, smem, st>>>(tmap, *fa, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2[scratch],
+                                                              eng->d_tile_cnt[scratch], eng->d_inv_scale, out);
     } else {
         if (smem > optin_plain) {
             BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -482,16 +483,17 @@ static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, 
         }
         FusedArgs none;
         memset(&none, 0, sizeof(none));
-        gebv_tc2_kernel<false><<<grid, T2_THREADS, smem, st>>>(tmap, none, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2,
-                                                               eng->d_tile_cnt, eng->d_inv_scale, out);
+        gebv_tc2_kernel<false><<<grid, T2_THREADS, smem, st>>>(tmap, none, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2[scratch],
+                                                               eng->d_tile_cnt[scratch], eng->d_inv_scale, out);
     }
     BG_LAUNCHED();
     return BG_OK;
 }
 
-int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st)
+// scratch: which of the two zero-invariant accumulator sets to use (two launches may be in flight on two streams)
+int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st, int scratch)
 {
-    return launch_tc2(eng, pop, nullptr, rows, out, st);
+    return launch_tc2(eng, pop, nullptr, rows, out, st, scratch);
 }
 
 // vector-env step: out_pop[e][i] = cross of pop[e][parents[e][i][0..1]] under mask[2i..2i+1]; gebv[e][i][T]
