@@ -468,18 +468,18 @@ static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, 
         eng->tile_cap[scratch] = (size_t)tiles;
     }
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
-    static size_t optin_fused = 48 * 1024, optin_plain = 48 * 1024;  // largest dynamic smem opted into so far
+    // largest dynamic smem opted into so far, per engine (= per device: the attribute is per device)
     if (fa) {
-        if (smem > optin_fused) {
+        if (smem > eng->tc2_optin[1]) {
             BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            optin_fused = smem;
+            eng->tc2_optin[1] = smem;
         }
         gebv_tc2_kernel<true><<<grid, T2F_THREADS, smem, st>>>(tmap, *fa, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2[scratch],
                                                               eng->d_tile_cnt[scratch], eng->d_inv_scale, out);
     } else {
-        if (smem > optin_plain) {
+        if (smem > eng->tc2_optin[0]) {
             BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            optin_plain = smem;
+            eng->tc2_optin[0] = smem;
         }
         FusedArgs none;
         memset(&none, 0, sizeof(none));

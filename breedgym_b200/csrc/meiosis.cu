@@ -266,13 +266,21 @@ __global__ void __launch_bounds__(256) blend_envs_kernel(const uint4 *__restrict
     if (HAS_MUT) U = __ldg(mut + q * W4 + v);
     const int e0 = blockIdx.z * env_chunk, e1 = min(E, e0 + env_chunk);
     constexpr int UN = 4;
+    // running pointers (one 64-bit add per env instead of re-deriving every address)
+    const int64_t pop_env = n_src * 2 * W4, out_env = rows * W4;
+    const int32_t *pp = parents + (int64_t)e0 * rows + q;
+    const uint4 *pe = pop + (int64_t)e0 * pop_env + v;
+    uint4 *oe = out + ((int64_t)e0 * rows + q) * W4 + v;
+    const int nsrc = (int)n_src, row2 = 2 * W4;
     for (int e = e0; e < e1; e += UN) {
         uint4 a[UN], b[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             if (e + u < e1) {
-                const int64_t s = norm_index(__ldg(parents + (int64_t)(e + u) * rows + q), n_src);
-                const uint4 *h0 = pop + ((int64_t)(e + u) * n_src + s) * 2 * W4 + v;
+                int s = __ldg(pp + (int64_t)u * rows);
+                s += s < 0 ? nsrc : 0;  // jnp indexing: negatives wrap once, then clamp
+                s = min(max(s, 0), nsrc - 1);
+                const uint4 *h0 = pe + u * pop_env + (int64_t)s * row2;
                 a[u] = __ldg(h0);
                 b[u] = __ldg(h0 + W4);
             }
@@ -284,9 +292,12 @@ __global__ void __launch_bounds__(256) blend_envs_kernel(const uint4 *__restrict
                 if (HAS_MUT) {
                     o.x ^= U.x; o.y ^= U.y; o.z ^= U.z; o.w ^= U.w;
                 }
-                out[((int64_t)(e + u) * rows + q) * W4 + v] = o;
+                oe[u * out_env] = o;
             }
         }
+        pp += (int64_t)UN * rows;
+        pe += UN * pop_env;
+        oe += UN * out_env;
     }
 }
 

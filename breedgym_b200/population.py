@@ -95,9 +95,11 @@ class PackedPopulation:
 
     def __getitem__(self, idx):
         if isinstance(idx, (int, np.integer)):
-            if self.words.dim() == 3:  # one individual: small, hand back the bool array
-                return PackedPopulation(self.sim, self.words[int(idx):int(idx) + 1 or None]).to_bool()[0]
-            return PackedPopulation(self.sim, self.words[int(idx)])
+            i = int(idx)
+            if self.words.dim() == 3:  # one individual: small, hand back its bool[m, 2] tensor
+                i = i + len(self) if i < 0 else i
+                return PackedPopulation(self.sim, self.words[i:i + 1]).to_bool()[0]
+            return PackedPopulation(self.sim, self.words[i])
         if isinstance(idx, slice):
             return PackedPopulation(self.sim, self.words[idx])
         if _is_int_index(idx) and self.words.dim() == 3:
