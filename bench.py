@@ -111,8 +111,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    res = cpu_steps(args.steps, args.warmup)
-    sample = (f"{res['steps']} full vector-env steps of {res['envs']} envs x {N_IND} x {N_MARKERS} "
+    # bounded sample: every step processes `envs` of the 64 envs of a GPU's share, chosen so that the whole
+    # --steps K --warmup W run stays around a minute whatever K is (throughput per env-step does not depend on it)
+    calib = cpu_steps(1, 0, envs=8)
+    per_env_step = 1.0 / calib["env_steps_per_sec"]
+    budget_s = 60.0
+    envs = int(max(1, min(ENVS_PER_GPU, budget_s / (per_env_step * max(1, args.steps + args.warmup)))))
+    res = cpu_steps(args.steps, args.warmup, envs=envs)
+    sample = (f"{res['steps']} vector-env steps of {res['envs']} envs x {N_IND} x {N_MARKERS} each "
               f"(cross + GEBV + reward), C oracle, OpenMP")
     line = {
         "impl": "reference",
@@ -176,8 +182,15 @@ class ClockSampler:
                 pass
             time.sleep(self.period)
 
+    def _sample_once(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        except Exception:
+            pass
+
     def start(self):
         if self.nv is not None:
+            self._sample_once()  # a short timed region may end before the thread's first tick
             self._thread = threading.Thread(target=self._loop, daemon=True)
             self._thread.start()
 
@@ -185,6 +198,8 @@ class ClockSampler:
         self._stop.set()
         if self._thread is not None:
             self._thread.join()
+        if self.nv is not None:
+            self._sample_once()
         return {
             "sm_mhz": float(np.median(self.samples)) if self.samples else None,
             "sm_max_mhz": self.max_mhz,

@@ -342,3 +342,53 @@ def test_wheat_breedgym_shapes(cuda_device):
     assert np.all(tru) and np.all(rews != 0)
     got = np.asarray(pop)
     assert np.array_equal(got[..., 0], got[..., 1])  # double haploids are homozygous
+
+
+def test_vec_env_edge_shapes_and_reward_shaping(cuda_device):
+    """One env (unique-key kernel path inside bg_vec_step), offspring count different from the parent count,
+    reward shaping on every step, device-resident infos, and bad action shapes."""
+    import torch
+
+    from breedgym_b200.vector import VecBreedGym
+
+    germ = np.load(GENOME)
+    for E in (1, 3):
+        env = VecBreedGym(num_envs=E, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=30,
+                          reward_shaping=True, num_generations=3)
+        pop, _ = env.reset(seed=5)
+        osim = oracle_sim(env.simulator, 5)
+        _, opops, _ = cr.vec_reset(germ, 30, E, jp.key(5))
+        rng = np.random.default_rng(E)
+        for n_off in (30, 17, 40):  # the population size follows the number of crosses
+            act = rng.integers(0, opops.shape[1], (E, n_off, 2))
+            pop, rews, ter, tru, infos = env.step(act)
+            opops = cr.vec_step(osim, opops, act)
+            g = cr.gebv(opops, osim.effects)
+            assert infos["GEBV"].shape == (E, n_off, 1)
+            assert np.allclose(rews, g.max(axis=(1, 2)), rtol=RTOL, atol=0)  # shaping: a reward on every step
+            if not tru[0]:
+                assert np.array_equal(np.asarray(pop), opops)
+        assert tru[0] and not ter[0]
+        with pytest.raises(ValueError):
+            env.step(np.zeros((E + 1, 30, 2), dtype=np.int64))
+        with pytest.raises(ValueError):
+            env.step(np.zeros((E, 30, 3), dtype=np.int64))
+    dev_env = VecBreedGym(num_envs=2, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=20, info_device="device")
+    dev_env.reset(seed=1)
+    _, rews, _, _, infos = dev_env.step(torch.randint(0, 20, (2, 20, 2), device="cuda"))
+    assert isinstance(infos["GEBV"], torch.Tensor) and infos["GEBV"].is_cuda and isinstance(rews, torch.Tensor)
+
+
+def test_empty_cross_and_single_offspring(cuda_device):
+    from breedgym_b200.simulator import Simulator
+
+    sim = Simulator(genetic_map=GMAP, device=0, seed=0)
+    pop = sim.as_packed(np.load(GENOME))
+    none = sim.cross(pop[np.zeros((0, 2), dtype=np.int64)])
+    assert none.shape == (0, 1000, 2) and sim.GEBV(none).shape == (0, 1)
+    one = sim.cross(pop[np.array([[3, 3]])])
+    assert one.shape == (1, 1000, 2)
+    # selfing a fully homozygous parent returns the parent
+    homo = np.repeat(np.load(GENOME)[:1, :, :1], 2, axis=2)
+    kid = sim.cross(sim.as_packed(homo)[np.array([[0, 0]])])
+    assert np.array_equal(np.asarray(kid), homo)
