@@ -431,6 +431,8 @@ static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *p
         if (rc) return rc;
         BG_CUDA(cudaStreamWaitEvent(st, eng->ev_half_done, 0));
     } else {
+        // blend and GEBV are adjacent in the stream (no event between them) so that the GEBV kernel's
+        // programmatic dependent launch can overlap its prologue with the blend's tail
         rc = bg_launch_blend(eng, pop, parents, sl.mask, eng->mut_thr ? sl.mut : nullptr, out, E, n_src, n, st);
         if (!rc && gebv_out) rc = bg_launch_gebv(eng, out, E * n, gebv_out, 0, st);
     }

@@ -191,6 +191,10 @@ __global__ void __launch_bounds__(FUSED ? T2F_THREADS : T2_THREADS, FUSED ? 3 : 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // Programmatic dependent launch: everything above (TMEM allocation, barrier init, row table) may overlap the
+    // tail of the kernel that produces this population; its memory is visible only past this point.  A no-op when
+    // the launch did not ask for programmatic stream serialization.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
     const uint32_t tmem_a = tmem_d + d_cols;
 
@@ -483,8 +487,22 @@ static int launch_tc2(bg_engine *eng, const uint32_t *pop, const FusedArgs *fa, 
         }
         FusedArgs none;
         memset(&none, 0, sizeof(none));
-        gebv_tc2_kernel<false><<<grid, T2_THREADS, smem, st>>>(tmap, none, rows, eng->d_wdig, N, T, steps, sps, eng->d_acc2[scratch],
-                                                               eng->d_tile_cnt[scratch], eng->d_inv_scale, out);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(T2_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int8_t *bd = eng->d_wdig;
+        const double *inv = eng->d_inv_scale;
+        unsigned long long *acc = eng->d_acc2[scratch];
+        unsigned int *cnt = eng->d_tile_cnt[scratch];
+        BG_CUDA(cudaLaunchKernelEx(&cfg, gebv_tc2_kernel<false>, tmap, none, rows, bd, N, T, steps, sps, acc, cnt, inv, out));
     }
     BG_LAUNCHED();
     return BG_OK;

@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(256) blend_envs_kernel(const uint4 *__restrict
                                                          uint4 *__restrict__ out, int E, int64_t n_src, int64_t rows,
                                                          int W4, int env_chunk)
 {
+    // let a dependent kernel (the GEBV of this population) start its prologue while this grid drains
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int v = blockIdx.y * blockDim.x + threadIdx.x;
     if (v >= W4) return;
     const int64_t q = blockIdx.x;
