@@ -392,3 +392,20 @@ def test_empty_cross_and_single_offspring(cuda_device):
     homo = np.repeat(np.load(GENOME)[:1, :, :1], 2, axis=2)
     kid = sim.cross(sim.as_packed(homo)[np.array([[0, 0]])])
     assert np.array_equal(np.asarray(kid), homo)
+
+
+def test_sharded_env_over_nccl_matches_unsharded(cuda_device):
+    """Two ranks on two GPUs (skipped on a single-GPU box): scripts/multi_gpu_check.py under torchrun."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(root / "scripts" / "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "multi-gpu check ok" in r.stdout
