@@ -544,6 +544,30 @@ int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_tot
     return bg_launch_reset_indices(eng, random_key, E_total, env_begin, E, n_germ, n, layout, idx_out, (cudaStream_t)stream);
 }
 
+int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, const uint32_t random_key[2], int64_t E_total,
+                 int64_t env_begin, int64_t E, int64_t n, int layout, int32_t *idx_dev, uint32_t *pop_out, float *gebv_dev,
+                 float *gebv_host, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(germplasm && random_key && idx_dev && pop_out && E > 0 && n > 0 && n_germ > 0, BG_EINVAL, "bg_vec_reset: bad argument");
+    BG_REQUIRE(env_begin >= 0 && env_begin + E <= E_total, BG_EINVAL, "bg_vec_reset: env range outside [0, E_total)");
+    BG_REQUIRE(!gebv_host || gebv_dev, BG_EINVAL, "bg_vec_reset: gebv_host needs gebv_dev");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = bg_launch_reset_indices(eng, random_key, E_total, env_begin, E, n_germ, n, layout, idx_dev, st);
+    if (rc) return rc;
+    rc = bg_launch_gather(germplasm, idx_dev, pop_out, E, n_germ, n, 0, eng->Wpad, st);
+    if (rc) return rc;
+    if (gebv_dev) {
+        rc = bg_launch_gebv(eng, pop_out, E * n, gebv_dev, 0, st);
+        if (rc) return rc;
+    }
+    if (gebv_host) {
+        BG_CUDA(cudaMemcpyAsync(gebv_host, gebv_dev, (size_t)E * n * eng->T * sizeof(float), cudaMemcpyDeviceToHost, st));
+        BG_CUDA(cudaStreamSynchronize(st));
+    }
+    return BG_OK;
+}
+
 // BG_TIMING=1: host-side wall time of each phase of bg_vec_step, printed every 1000 calls (diagnostics)
 struct StepTimer {
     bool on;

@@ -31,7 +31,10 @@ constexpr int T2_KS = 128;          // markers per step (4 words per plane, 32 T
 #define T2_S_VAL 3
 #endif
 constexpr int T2_S = T2_S_VAL;      // A (TMEM) / B (smem) stages
-constexpr int T2_R = 4;             // raw macro-tile ring
+#ifndef T2_R_VAL
+#define T2_R_VAL 4
+#endif
+constexpr int T2_R = T2_R_VAL;      // raw macro-tile ring
 constexpr int T2_SPM = 1;           // steps per raw macro tile (4 = 64-byte TMA rows measured slower: 38 vs 34.6 us at C2)
 constexpr int T2_THREADS = 256 + 64;
 constexpr int T2F_THREADS = T2_THREADS + 128;   // fused: + 4 blender warps
@@ -205,20 +208,25 @@ __global__ void __launch_bounds__(FUSED ? T2F_THREADS : T2_THREADS, FUSED ? 3 : 
         // per-step tail shared by both variants: dosage bytes of 4 words per plane -> A stage in TMEM
         auto expand_step = [&](int j, const uint4 x0, const uint4 x1) {
             const int as = j % T2_S;
+            // dosages as 2-bit fields first (even / odd markers: field f of ze <-> marker 2f, of zo <-> 2f+1; a field
+            // holds 0..2, no carry) -- done BEFORE waiting for the TMEM stage, so this work hides the MMA's latency
+            const uint32_t w0[4] = {x0.x, x0.y, x0.z, x0.w}, w1[4] = {x1.x, x1.y, x1.z, x1.w};
+            uint32_t ze[4], zo[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                ze[jj] = (w0[jj] & 0x55555555u) + (w1[jj] & 0x55555555u);
+                zo[jj] = ((w0[jj] >> 1) & 0x55555555u) + ((w1[jj] >> 1) & 0x55555555u);
+            }
             if (j >= T2_S) mbar_wait(smem_u32(&bars.a_empty[as]), ((j / T2_S) - 1) & 1);  // MMAs of the previous use retired
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t w0[4] = {x0.x, x0.y, x0.z, x0.w}, w1[4] = {x1.x, x1.y, x1.z, x1.w};
             const uint32_t ta = tmem_a + lane_sel + (uint32_t)as * (T2_KS / 4);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                // dosages as 2-bit fields first (even / odd markers: field f of ze <-> marker 2f, of zo <-> 2f+1; a
-                // field holds 0..2, no carry), then one shift + mask lifts 4 fields into 4 bytes:
-                // column q, byte b <-> K index 4q + b <-> marker 8b + q of this word.  22 integer ops per 32 markers.
-                const uint32_t ze = (w0[jj] & 0x55555555u) + (w1[jj] & 0x55555555u);
-                const uint32_t zo = ((w0[jj] >> 1) & 0x55555555u) + ((w1[jj] >> 1) & 0x55555555u);
+                // one shift + mask lifts 4 fields into 4 bytes: column q, byte b <-> K index 4q + b <-> marker 8b + q
+                // of this word.  22 integer ops per 32 markers in total.
                 uint32_t o[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] = (((q & 1) ? zo : ze) >> (q & ~1)) & 0x03030303u;
+                for (int q = 0; q < 8; ++q) o[q] = (((q & 1) ? zo[jj] : ze[jj]) >> (q & ~1)) & 0x03030303u;
                 tmem_st8(ta + 8 * jj, o);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

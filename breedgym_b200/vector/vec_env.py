@@ -227,20 +227,27 @@ class VecBreedGym(VectorEnv):
 
         begin, total = self.env_shard
         sim, E, n = self.simulator, self.num_envs, self.individual_per_gen
+        T = sim.GEBV_model.n_traits
         key = np.ascontiguousarray(self.random_key, dtype=np.uint32)
         idx = torch.empty((E, n), dtype=torch.int32, device=self.device)
-        lib = _lib.load()
-        # env g draws permutation(keys[1 + g], N)[:n] with keys = split(random_key, total + 1)
-        _lib.check(lib.bg_reset_indices(sim._engine, _lib.nptr(key), total, begin, E, len(self.germplasm), n,
-                                        sim._layout(), idx.data_ptr(), sim._stream()))
-        self.random_key = _lib.key_split_at(self.random_key, 0, total + 1, sim.rng_layout)
         words = sim._empty_words(E, n)
         germ = self.germplasm.words.contiguous()
-        _lib.check(lib.bg_gather_individuals(sim._engine, germ.data_ptr(), idx.data_ptr(), words.data_ptr(), E,
-                                             germ.shape[0], n, 0, sim._stream()))
+        host_info = self.info_device == "host"
+        if host_info:
+            io = self._host_io((E, n, 2), T)
+            gebv_dev_ptr, gebv_host_ptr = io["gebv_dev"], io["gebv_pin"]
+        else:
+            gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
+            gebv_dev_ptr, gebv_host_ptr = gebv_dev.data_ptr(), None
+        # env g draws permutation(keys[1 + g], N)[:n] with keys = split(random_key, total + 1); one C call does
+        # the draw, the gather from the germplasm and the reset infos
+        _lib.check(_lib.load().bg_vec_reset(sim._engine, germ.data_ptr(), germ.shape[0], _lib.nptr(key), total, begin, E, n,
+                                            sim._layout_id, idx.data_ptr(), words.data_ptr(), gebv_dev_ptr, gebv_host_ptr,
+                                            sim._stream()))
+        self.random_key = _lib.key_split_at(self.random_key, 0, total + 1, sim.rng_layout)
         self._reset_indices = idx
         self.populations = PackedPopulation(sim, words)
-        self.reset_infos = self.get_info()
+        self.reset_infos = {"GEBV": io["gebv_np"].copy() if host_info else gebv_dev}
         return self.populations, self.reset_infos
 
     def get_info(self) -> dict:

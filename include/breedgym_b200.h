@@ -160,6 +160,14 @@ int bg_reduce_mean(bg_engine *eng, const float *gebv, int64_t E, int64_t per_env
 int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_total, int64_t env_begin, int64_t E,
                      int64_t n_germ, int64_t n, int layout, int32_t *idx_out, void *stream);
 
+/* VecBreedGym.reset in one call (breedgym/vector/vec_env.py:109-130): bg_reset_indices, the gather
+ * of the drawn individuals from the germplasm (packed [n_germ][2][Wpad]) into pop_out
+ * ([E][n][2][Wpad]) and, when gebv_dev is non-NULL, the reset infos GEBV_model(populations)
+ * ([E][n][T]); gebv_host non-NULL copies them to the host and synchronises the stream. */
+int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, const uint32_t random_key[2], int64_t E_total,
+                 int64_t env_begin, int64_t E, int64_t n, int layout, int32_t *idx_dev, uint32_t *pop_out, float *gebv_dev,
+                 float *gebv_host, void *stream);
+
 /* ---- one-call vector-env step ------------------------------------------------
  * VecBreedGym.step hot path (breedgym/vector/vec_env.py:88-100) with host
  * buffers at the boundary: copies actions_host (int32 [E][n][2], pinned or
