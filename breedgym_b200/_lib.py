@@ -31,6 +31,7 @@ _SIGNATURES = {
     "bg_key_split": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
     "bg_key_split_at": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "bg_random_bits": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
+    "bg_shuffle_sort_keys": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "bg_key_chain_next": (c_int, [c_void_p, c_int, c_void_p]),
     "bg_thresholds": (c_int, [c_void_p, c_int64, c_void_p]),
     "bg_words_per_row": (c_int64, [c_int64]),

@@ -115,6 +115,23 @@ int bg_key_split_at(const uint32_t key[2], int64_t index, int64_t num, int layou
     return BG_OK;
 }
 
+int bg_shuffle_sort_keys(const uint32_t *keys, int64_t E, int64_t n, int layout, int rounds, uint32_t *out)
+{
+    BG_REQUIRE(keys && out && E >= 0 && n >= 0 && rounds >= 0, BG_EINVAL, "bg_shuffle_sort_keys: bad argument");
+    BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
+    for (int64_t e = 0; e < E; ++e) {
+        TfKey key = tf_make_key(keys[2 * e], keys[2 * e + 1]);
+        for (int r = 0; r < rounds; ++r) {
+            // jax _shuffle: key, subkey = split(key); sort_keys = random_bits(subkey, n)
+            const TfKey sub = tf_split_at(key, 1, 2, layout);
+            key = tf_split_at(key, 0, 2, layout);
+            uint32_t *o = out + ((int64_t)r * E + e) * n;
+            for (int64_t j = 0; j < n; ++j) o[j] = tf_bits_at(sub, (uint64_t)j, (uint64_t)n, layout);
+        }
+    }
+    return BG_OK;
+}
+
 int bg_random_bits(const uint32_t key[2], int64_t n, int layout, uint32_t *out)
 {
     BG_REQUIRE(key && out && n >= 0, BG_EINVAL, "bg_random_bits: bad argument");

@@ -29,6 +29,18 @@ def permutation(key: np.ndarray, n: int, layout: str = "legacy") -> np.ndarray:
     return x
 
 
+def permutation_batch(keys: np.ndarray, n: int, layout: str = "legacy") -> np.ndarray:
+    """`vmap(jax.random.permutation)(keys, n)` for keys `[E, 2]` -> int64 `[E, n]`, vectorised over E."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    E, rounds = keys.shape[0], shuffle_rounds(n)
+    sort_keys = np.empty((rounds, E, n), dtype=np.uint32)
+    _lib.check(_lib.load().bg_shuffle_sort_keys(_lib.nptr(keys), E, n, _lib.LAYOUT_ID[layout], rounds, _lib.nptr(sort_keys)))
+    x = np.broadcast_to(np.arange(n, dtype=np.int64), (E, n))
+    for r in range(rounds):
+        x = np.take_along_axis(x, np.argsort(sort_keys[r], axis=1, kind="stable"), axis=1)
+    return np.ascontiguousarray(x)
+
+
 def choice_no_replace(key: np.ndarray, n_inputs: int, n_draws: int, layout: str = "legacy") -> np.ndarray:
     if n_draws > n_inputs:
         raise ValueError("Cannot take a larger sample than population when 'replace=False'")

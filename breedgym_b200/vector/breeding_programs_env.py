@@ -26,8 +26,8 @@ class WheatBreedGym(VectorWrapper):
         self.single_action_space = spaces.Box(-1e5, 1e5, shape=action_shape)
         self.action_space = spaces.Box(-1e5, 1e5, shape=(self.num_envs, *action_shape))
 
-    def _convert_actions(self, actions: np.ndarray) -> np.ndarray:
-        return np.stack([_pairs_from_scores(a, self.n_lines) for a in actions]).astype(np.int32)
+    def _convert_actions(self, actions) -> torch.Tensor:
+        return _pairs_from_scores(actions, self.n_lines, self.device)
 
     def _index(self, pop: PackedPopulation) -> torch.Tensor:
         return self.simulator.GEBV_model(pop).sum(dim=-1)
@@ -51,7 +51,7 @@ class WheatBreedGym(VectorWrapper):
     def step(self, actions):
         env, sim = self.env, self.simulator
         E = self.num_envs
-        pairs = self._convert_actions(_to_host(actions))
+        pairs = self._convert_actions(actions)
         pop = self.cross(pairs)  # [E, n_lines]
         assert pop.shape[1] == self.n_lines
 

@@ -3,8 +3,10 @@
 Mirrors breedgym/vector/vec_wrappers.py:15-155: `SelectionScores` (scores ->
 top-k -> random subset of the diallel -> repeat), `PairScores` (n x n pair scores
 -> top-n pairs, softmax-proportional offspring counts) and `RavelIndex`.  The
-index math runs on the host (`breedgym_b200.jaxlike`); the resulting
-`int32[E, n, 2]` pairs feed the unchanged `VecBreedGym.step` hot path.
+index math is batched over the envs: `SelectionScores` on the host (NumPy + the
+library's Threefry for the jax-compatible permutations), `PairScores` on the GPU
+(a stable sort of the E x n^2 scores); the resulting `int32[E, n, 2]` pairs feed
+the unchanged `VecBreedGym.step` hot path.
 """
 from __future__ import annotations
 
@@ -54,16 +56,23 @@ class SelectionScores(VectorWrapper):
         self.single_action_space = spaces.Box(-1e5, 1e5, shape=(self.individual_per_gen,))
         self.action_space = spaces.Box(-1e5, 1e5, shape=(self.num_envs, self.individual_per_gen))
 
-    def _convert_action(self, action: np.ndarray, random_key: np.ndarray) -> np.ndarray:
-        n = self.individual_per_gen
-        _, best_pop = jaxlike.top_k(action, self.k)
-        diallel = Simulator._diallel_indices(best_pop)
-        sel = jaxlike.choice_no_replace(random_key, len(diallel), self.n_crosses, self.simulator.rng_layout)
-        cross_indices = diallel[sel]
-        return jaxlike.repeat_total(cross_indices, int(ceil(n / self.n_crosses)), n)
-
     def _convert_actions(self, actions: np.ndarray, random_keys: np.ndarray) -> np.ndarray:
-        return np.stack([self._convert_action(a, k) for a, k in zip(actions, random_keys)]).astype(np.int32)
+        """Scores `[E, n]` + one key per env -> parent pairs `int32[E, n, 2]`, vectorised over the envs:
+        top-k (ties -> lower index), the k(k-1)/2 pairs of the best in upper-triangular order, a random subset of
+        `n_crosses` of them (`jax.random.choice(replace=False)` = first entries of a permutation) and each pair
+        repeated ceil(n / n_crosses) times, cut to n."""
+        n = self.individual_per_gen
+        _, best = jaxlike.top_k(np.asarray(actions), self.k)                       # [E, k]
+        ia, ib = np.triu_indices(self.k, k=1)
+        diallel = np.stack([best[:, ia], best[:, ib]], axis=-1)                    # [E, C(k,2), 2]
+        if self.n_crosses > diallel.shape[1]:
+            raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+        perm = jaxlike.permutation_batch(random_keys, diallel.shape[1], self.simulator.rng_layout)
+        chosen = np.take_along_axis(diallel, perm[:, : self.n_crosses, None], axis=1)  # [E, n_crosses, 2]
+        out = np.repeat(chosen, int(ceil(n / self.n_crosses)), axis=1)[:, :n]
+        if out.shape[1] < n:  # jnp.repeat(total_repeat_length=n) pads with the last entry
+            out = np.concatenate([out, np.repeat(out[:, -1:], n - out.shape[1], axis=1)], axis=1)
+        return np.ascontiguousarray(out, dtype=np.int32)
 
     def step(self, actions):
         begin, total = self.env.env_shard
@@ -74,12 +83,22 @@ class SelectionScores(VectorWrapper):
         return super().step(low_level_actions)
 
 
-def _pairs_from_scores(action: np.ndarray, n_crosses: int) -> np.ndarray:
-    """Top-n pairs of an n x n score matrix with softmax-proportional offspring counts."""
-    best_values, best_crosses = jaxlike.top_k(action.reshape(-1), n_crosses)
-    offspring_per_cross = jaxlike.softmax_f32(best_values) * np.float32(n_crosses)
-    cross_indices = np.stack((best_crosses // n_crosses, best_crosses % n_crosses), axis=1)
-    return jaxlike.repeat_total(cross_indices, np.ceil(offspring_per_cross).astype(np.int32), n_crosses)
+def _pairs_from_scores(scores, n_crosses: int, device) -> torch.Tensor:
+    """Pair scores `[E, n, n]` -> parent pairs `int32[E, n_crosses, 2]` on the GPU.
+
+    Per env (breedgym/vector/vec_wrappers.py:100-112): the n_crosses best pairs (descending, ties -> lower flat
+    index), offspring per pair = ceil(softmax(best values) * n_crosses), `jnp.repeat(..., total_repeat_length=n_crosses)`
+    (truncate, or pad with the last pair)."""
+    s = torch.as_tensor(scores, dtype=torch.float32, device=device)
+    E, n = s.shape[0], s.shape[-1]
+    vals, idx = torch.sort(s.reshape(E, -1), dim=1, descending=True, stable=True)
+    vals, idx = vals[:, :n_crosses], idx[:, :n_crosses]
+    reps = torch.ceil(torch.softmax(vals, dim=1) * n_crosses).to(torch.int64)
+    ends = torch.cumsum(reps, dim=1)  # pair b fills output slots [ends[b-1], ends[b])
+    slots = torch.arange(n_crosses, device=s.device).expand(E, n_crosses).contiguous()
+    which = torch.searchsorted(ends, slots, right=True).clamp_(max=n_crosses - 1)
+    flat = torch.gather(idx, 1, which)
+    return torch.stack((flat // n, flat % n), dim=-1).to(torch.int32)
 
 
 class PairScores(VectorWrapper):
@@ -93,13 +112,13 @@ class PairScores(VectorWrapper):
         self.single_action_space = spaces.Box(-1e5, 1e5, shape=action_shape)
         self.action_space = spaces.Box(-1e5, 1e5, shape=(self.num_envs, *action_shape))
 
-    def _convert_actions(self, actions: np.ndarray) -> np.ndarray:
-        return np.stack([_pairs_from_scores(a, self.n_crosses) for a in actions]).astype(np.int32)
+    def _convert_actions(self, actions) -> torch.Tensor:
+        return _pairs_from_scores(actions, self.n_crosses, self.device)
 
     def step(self, actions):
-        low_level_actions = self._convert_actions(_to_host(actions))
+        low_level_actions = self._convert_actions(actions)
         obs, rew, ter, tru, infos = super().step(low_level_actions)
-        infos["low_level_actions"] = low_level_actions
+        infos["low_level_actions"] = low_level_actions.cpu().numpy()
         return obs, rew, ter, tru, infos
 
 

@@ -63,6 +63,10 @@ int bg_key_split(const uint32_t key[2], int64_t num, int layout, uint32_t *out /
 /* element `index` of split(key, num) without computing the others (vec_env.py:120-121 keeps keys[0] only) */
 int bg_key_split_at(const uint32_t key[2], int64_t index, int64_t num, int layout, uint32_t out[2]);
 int bg_random_bits(const uint32_t key[2], int64_t n, int layout, uint32_t *out /* [n] */);
+/* sort keys of jax.random.permutation / choice(replace=False) for E independent keys at once
+ * (breedgym/vector/vec_wrappers.py:68-70): per key and round, key, sub = split(key);
+ * out[r][e][:] = random_bits(sub, n).  keys: [E][2], out: [rounds][E][n] */
+int bg_shuffle_sort_keys(const uint32_t *keys, int64_t E, int64_t n, int layout, int rounds, uint32_t *out);
 /* one link of chromax's chain `random_key, k = split(random_key)`: state <- split(state)[0],
  * out[0..1] = k, out[2..3] = the k the NEXT call will return (lookahead for bg_vec_step) */
 int bg_key_chain_next(uint32_t state[2], int layout, uint32_t out[4]);

@@ -94,6 +94,11 @@ def test_jaxlike_matches_oracle(golden):
         for n, k in ((45, 20), (10, 10), (1, 1)):
             assert np.array_equal(jaxlike.choice_no_replace(_lib.key_data(3), n, k, layout),
                                   jp.choice_no_replace(jp.key(3), n, k, layout))
+        keys = jp.split(jp.key(8), 4, layout)
+        for n in (45, 2000):  # one and two shuffle rounds
+            batch = jaxlike.permutation_batch(keys, n, layout)
+            for e in range(4):
+                assert np.array_equal(batch[e], jp.permutation(keys[e], n, layout))
     with pytest.raises(ValueError):
         jaxlike.choice_no_replace(_lib.key_data(3), 1, 10)
     x = np.array([[1.0, 3.0, 3.0, 2.0], [0.0, -1.0, 5.0, 5.0]])
@@ -104,6 +109,25 @@ def test_jaxlike_matches_oracle(golden):
     assert np.array_equal(jaxlike.repeat_total(a, 1, 5), jp.repeat_total(a, 1, 5))
     s = jaxlike.softmax_f32(np.array([1.0, 2.0, 3.0]))
     assert s.dtype == np.float32 and abs(s.sum() - 1) < 1e-6
+
+
+def test_pair_scores_conversion_matches_per_env_composition():
+    """PairScores' batched conversion (torch; runs on the GPU in production) == top_k / softmax / repeat per env."""
+    import torch
+
+    from breedgym_b200 import jaxlike
+    from breedgym_b200.vector.vec_wrappers import _pairs_from_scores
+    from oracle import jax_prng as jp
+
+    rng = np.random.default_rng(0)
+    n = 12
+    sc = rng.standard_normal((3, n, n)).astype(np.float32)
+    sc[1, 2, 3] = sc[1, 0, 0] = sc[1].max() + 1  # a tie for the top pair: lower flat index first
+    got = _pairs_from_scores(torch.from_numpy(sc), n, "cpu").numpy()
+    for e in range(3):
+        v, i = jp.top_k(sc[e].reshape(-1), n)
+        reps = np.ceil(jaxlike.softmax_f32(v) * np.float32(n)).astype(np.int32)
+        assert np.array_equal(got[e], jp.repeat_total(np.stack((i // n, i % n), 1), reps, n))
 
 
 def test_gym_shim_semantics():
