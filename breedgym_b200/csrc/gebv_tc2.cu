@@ -75,10 +75,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"  // sleeps up to %3 ns unless the phase completes
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(2000u)
             : "memory");
         if (spin > T2_SPIN_LIMIT) __trap();
     }

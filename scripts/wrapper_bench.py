@@ -14,7 +14,7 @@ from breedgym_b200.vector import PairScores, SelectionScores, VecBreedGym  # noq
 germ = np.random.default_rng(0).random((370, 10000, 2)) < 0.5
 kw = dict(num_envs=64, initial_population=germ, genetic_map=ROOT / "breedgym_b200/data/small_genetic_map.txt",
           trait_names=["Yield"], individual_per_gen=370, device=0)
-for name, make in (("SelectionScores", lambda: SelectionScores(VecBreedGym(**kw), k=37)),
+for name, make in (("SelectionScores", lambda: SelectionScores(VecBreedGym(**kw), k=20)),
                    ("PairScores", lambda: PairScores(VecBreedGym(**kw)))):
     env = make()
     _, infos = env.reset(seed=7)
