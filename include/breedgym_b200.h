@@ -143,8 +143,8 @@ int bg_meiosis_masks(bg_engine *eng, uint32_t *mask_out, int64_t rows, const uin
  * Arithmetic: exact 64-bit fixed point of the float32 effects, one final rounding
  * to float32 (deterministic; differs from a float64 dot by < 1 ulp of float32). */
 int bg_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, void *stream);
-/* same result through the straightforward bit-test kernel (cross-check / fallback
- * shapes); algorithm id: 0 auto, 1 direct bit-test, 2 byte-LUT, 3 tcgen05 int8 GEMM
+/* bg_gebv with an explicit kernel choice (cross-checks, tuning, > 32 traits);
+ * algorithm id: 0 auto, 1 direct bit-test, 2 byte-LUT, 3 tcgen05 int8 GEMM
  * (TMA loads, dosage operand in tensor memory), 4 tcgen05 int8 GEMM (operand staged in shared
  * memory).  All produce the same 64-bit integers. */
 int bg_gebv_algo(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, int algo, void *stream);
