@@ -242,7 +242,8 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
     BG_CUDA(cudaMemcpy(eng->d_thr, thr.data(), nthr * sizeof(uint32_t), cudaMemcpyHostToDevice));
 
     if (n_traits > 0) {
-        // fixed point: w_fix = rint(w * 2^s), s = largest shift with 2*sum|w| * 2^s < 2^61
+        // fixed point: w_fix = rint(w * 2^s), s = largest shift with 2*sum|w| * 2^s < 2^55 (the tensor-core kernels
+        // sum 64x these integers, see the digit table below, and must stay inside int64)
         const size_t stride = (size_t)((eng->Wpad + 7) / 8) * 256;
         std::vector<long long> wfix(stride * n_traits, 0ll);
         std::vector<double> inv(n_traits, 1.0);
@@ -257,7 +258,7 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
             if (sum > 0.0) {
                 int ex;
                 frexp(2.0 * sum, &ex);  // 2*sum < 2^ex
-                s = 61 - ex;
+                s = 55 - ex;
                 if (s > 1000) s = 1000;
                 if (s < -1000) s = -1000;
             }
@@ -273,6 +274,10 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
         // tensor-core digit table: w_fix = sum_d digit_d * 256^d with balanced digits in [-128,127],
         // stored per 128-marker step as [N/8][8][8 rows][16 B] core matrices (gebv_tc*.cu).  Inside
         // a 32-marker word, K index 4*s + b holds marker 8*b + s (matches the kernels' expansion).
+        // PRESCALED operand: the kernels feed the dosage of marker 8*b + s as the unsigned byte
+        // dosage * 4^(s/2) (a masked 2-bit field left where it sits in its byte: one LOP3, no shift),
+        // so the digits here are those of w_fix * 4^(3 - s/2) and every tensor-core sum is exactly
+        // 64x the plain fixed-point sum (shifted back in the kernels' epilogues).
         eng->tc_N = 0;
         eng->tc_steps = 0;
         if (n_traits <= bg_gebv_tc_max_traits()) {
@@ -285,6 +290,7 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
                     if (w == 0) continue;
                     const int64_t st = j / 128;
                     const int word = (int)(j % 128) / 32, bit = (int)(j % 32);
+                    w *= 1ll << (2 * (3 - (bit % 8) / 2));
                     const int k = word * 32 + 4 * (bit % 8) + bit / 8;
                     for (int d = 0; d < 8; ++d) {
                         const int dgt = (int)(((w + 128) & 255) - 128);

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS) gebv_tc_kernel(const uint32_t *__r
                 uint32_t o[8];
 #pragma unroll
                 for (int sft = 0; sft < 8; ++sft)  // byte b of o[sft] <-> marker 8b + sft of this word
-                    o[sft] = ((w0[jj] >> sft) & 0x01010101u) + ((w1[jj] >> sft) & 0x01010101u);
+                    o[sft] = (((w0[jj] >> sft) & 0x01010101u) + ((w1[jj] >> sft) & 0x01010101u)) << (sft & ~1);  // prescaled: dosage * 4^(sft/2)
                 const uint32_t dst = a_base + a_row_off + (uint32_t)(2 * (4 * half + jj)) * 128;
                 sts128(dst, o[0], o[1], o[2], o[3]);
                 sts128(dst + 128, o[4], o[5], o[6], o[7]);
@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS) gebv_tc_kernel(const uint32_t *__r
     } else if (lane == 0) {
         // ---------------- MMA issuer ----------------
         // instruction descriptor: D = S32, A = B = signed 8-bit, both K-major, N, M = 128
-        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+        // A = unsigned 8-bit (prescaled dosage bytes reach 128), B = signed 8-bit digits, D = int32
+        const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
         const uint32_t b_bytes = (uint32_t)(N * TC_KC);
         for (int it = 0; it < nch; ++it) {
             const int s = it % TC_STAGES, use = it / TC_STAGES;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS) gebv_tc_kernel(const uint32_t *__r
             unsigned long long sum = 0;  // modular arithmetic: the true total fits in int64
 #pragma unroll
             for (int d = 7; d >= 0; --d) sum = (sum << 8) + (unsigned long long)(long long)(int32_t)v[d];
-            if (row < rows) dst[t] = (long long)sum;
+            if (row < rows) dst[t] = (long long)sum >> 6;  // the prescaled operand makes every sum exactly 64x (api.cu)
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -284,6 +285,9 @@ int bg_launch_gebv_tc(bg_engine *eng, const uint32_t *pop, int64_t rows, float *
     const int max_split = (chunks + 7) / 8;
     if (ksplit > max_split) ksplit = max_split;
     if (ksplit < 1) ksplit = 1;
+    // int32 accumulators: a 256-marker chunk adds at most 2 * 16 * 43520 to a digit sum (prescaled bytes <= 128,
+    // |digit| <= 128), so at most 1500 chunks per CTA keeps every digit sum below 2^31
+    if (ksplit < (chunks + 1499) / 1500) ksplit = (chunks + 1499) / 1500;
     if (ksplit > 65535) ksplit = 65535;
     int cps = (chunks + ksplit - 1) / ksplit;
     ksplit = (chunks + cps - 1) / cps;
