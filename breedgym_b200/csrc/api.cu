@@ -156,7 +156,9 @@ int bg_thresholds(const float *r, int64_t m, uint32_t *out)
     return BG_OK;
 }
 
-int64_t bg_words_per_row(int64_t n_markers) { return ((n_markers + 31) / 32 + 3) / 4 * 4; }
+// row pitch: a multiple of 32 words, so every bit-plane row starts on a 128-byte line (whole sectors for the
+// 32-byte gathers of the fused step kernel, whole lines for the coalesced blend and the TMA boxes)
+int64_t bg_words_per_row(int64_t n_markers) { return ((n_markers + 31) / 32 + 31) / 32 * 32; }
 
 int bg_engine_create(int device, bg_engine **out)
 {

@@ -29,7 +29,7 @@ struct bg_engine {
     // map constants
     int64_t m = 0;       // markers
     int32_t W = 0;       // ceil(m/32)
-    int32_t Wpad = 0;    // W rounded up to a multiple of 4
+    int32_t Wpad = 0;    // W rounded up to a multiple of 32 (128-byte rows)
     int32_t T = 0;       // traits
     uint32_t *d_thr = nullptr;        // [Wpad*32 + 32] recombination thresholds (zero padded)
     uint32_t mut_thr = 0;             // mutation threshold (0 = off)

@@ -18,7 +18,7 @@
  *     void*); nothing synchronises unless stated.  One engine per (device,thread).
  *   - packed population layout: uint32 words [rows][2][Wpad], haplotype-major bit
  *     planes, marker j <-> bit (j & 31) of word (j >> 5), Wpad = bg_words_per_row(m)
- *     (ceil(m/32) rounded up to a multiple of 4 => rows are 16-byte aligned);
+ *     (ceil(m/32) rounded up to a multiple of 32 => every row starts on a 128-byte line);
  *     padding bits are zero.  The reference's byte layout `bool[rows][m][2]`
  *     (breedgym/breedgym.py:47, vec_env.py:57-62) appears only at bg_pack/bg_unpack.
  */

@@ -82,7 +82,7 @@ def test_thresholds_match_float_compare():
 def test_words_per_row():
     from breedgym_b200 import _lib
 
-    assert [_lib.words_per_row(m) for m in (1, 32, 33, 128, 129, 10000, 1000000)] == [4, 4, 4, 4, 8, 316, 31252]
+    assert [_lib.words_per_row(m) for m in (1, 32, 33, 128, 129, 10000, 1000000)] == [32, 32, 32, 32, 32, 320, 31264]
 
 
 def test_jaxlike_matches_oracle(golden):
