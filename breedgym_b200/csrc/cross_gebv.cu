@@ -5,23 +5,26 @@
 // 2x-population parent gather is never materialised.  Algorithmic HBM traffic: 0.75 B per offspring-marker
 //  -- the separate blend + GEBV pass pays 1.0 B.
 //
-// One CTA = 128 offspring x a K range of 128-marker steps (same tile / K-split / exact int8 digit GEMM as
-// gebv_tc2.cu).  Warp roles:
+// One CTA = 128 offspring x a K range of 128-marker steps (same K-split / exact int8 digit GEMM as gebv_tc2.cu).
+// The 128 offspring of a tile are taken CHILD-major: tile row R <-> (child i = R / E, env e = R % E).  The crossover
+// masks depend on the child slot only (the reference shares one key across envs, vec_env.py:75-77), so with E a
+// multiple of 32 all lanes of a warp read the SAME mask words: one broadcast L1/L2 access per warp instead of a
+// third of the kernel's gather traffic.  Warp roles:
 //
-//   warps 11-14 (loaders)   : cp.async (LDGSTS) 16-byte copies, two lanes per 32-byte sector: for every offspring
-//                             row the two bit planes of parent A, of parent B and the two mask rows -> a ring of
-//                             stages [6 chunks][128 rows][32 B = 2 steps] in shared memory (16-byte halves
-//                             XOR-swizzled with the row so the one-row-per-lane reads below are conflict free).
-//                             Nothing waits on a scoreboard: completion lands on an mbarrier
+//   warps 11-14 (loaders)   : cp.async (LDGSTS) 16-byte copies, four lanes per 64-byte row segment: the two bit
+//                             planes of parent A and of parent B of every offspring -> a ring of stages
+//                             [4 chunks][128 rows][64 B = 4 steps] in shared memory (16-byte quarters XOR-swizzled
+//                             with the row, so the one-row-per-lane reads below are conflict free).  Nothing
+//                             waits on a scoreboard: completion lands on an mbarrier
 //                             (cp.async.mbarrier.arrive.noinc), so the bytes in flight are bounded by the ring
-//                             (3 x 24 KB per CTA), not by registers.
-//   warps 0-7  (expanders)  : thread t <-> offspring t of the tile <-> TMEM lane t.  6 x ld.shared.v4, one LOP3
-//                             per word selects the alleles (h0 & ~M | h1 & M), the offspring words go to an
-//                             output stage in shared memory, then 4 words per plane -> 128 prescaled dosage bytes
-//                             -> tcgen05.st into the A stage in tensor memory.
-//   warp 10    (storer)     : cp.async.bulk.tensor (TMA store, one [128 rows x 32 B] box per plane and stage)
-//                             writes the offspring to HBM, coalesced, off every thread's critical path.
-//   warp 8     (digits)     : 1-D bulk copies of the digit tiles.
+//                             (2 x 32 KB per CTA, 2 CTAs per SM), not by registers.
+//   warps 0-7  (expanders)  : thread t <-> offspring t of the tile <-> TMEM lane t; the two groups of 4 warps take
+//                             alternate steps.  4 x ld.shared.v4 + the two mask quads (prefetched one step ahead
+//                             with ld.global.nc), one LOP3 per word selects the alleles (h0 & ~M | h1 & M), the
+//                             offspring words go to an output stage in shared memory, then 4 words per plane ->
+//                             128 prescaled dosage bytes -> tcgen05.st into the A stage in tensor memory.
+//   warp 10    (storer)     : output stage -> HBM, four lanes per 64-byte row segment (coalesced 128-bit stores).
+//   warp 8     (digits)     : 1-D bulk copies (TMA) of the digit tiles.
 //   warp 9     (MMA)        : tcgen05.mma.kind::i8, A from TMEM, B from shared memory, D in TMEM.
 //   warps 0-3  (epilogue)   : digits -> int64 -> K-split atomics -> float32 (tc_common.cuh).
 #include <cuda.h>
@@ -35,7 +38,7 @@ using namespace bgtc;
 namespace {
 
 #ifndef XG_R_VAL
-#define XG_R_VAL 3
+#define XG_R_VAL 2
 #endif
 #ifndef XG_S_VAL
 #define XG_S_VAL 4
@@ -46,15 +49,18 @@ namespace {
 #ifndef XG_CTAS_VAL
 #define XG_CTAS_VAL 2
 #endif
-constexpr int XG_R = XG_R_VAL;        // input ring (stages of 2 steps)
+constexpr int XG_R = XG_R_VAL;        // input ring (stages of 4 steps)
 constexpr int XG_S = XG_S_VAL;        // A (TMEM) / B (smem) stages (steps)
-constexpr int XG_OR = XG_OR_VAL;      // output ring (stages of 2 steps)
+constexpr int XG_OR = XG_OR_VAL;      // output ring (stages of 4 steps)
 constexpr int XG_CTAS = XG_CTAS_VAL;  // CTAs per SM
+constexpr int XG_SPS = 4;             // steps per stage: 64 B per row and plane
 constexpr int XG_LOADER_WARP0 = 11, XG_LOADERS = 128;
 constexpr int XG_THREADS = (XG_LOADER_WARP0 + 4) * 32;
-constexpr uint32_t XG_CHUNK = TILE_M * 32;        // one chunk of a stage: 128 rows x 32 B
-constexpr uint32_t XG_IN_BYTES = 6 * XG_CHUNK;    // parent A planes 0/1, parent B planes 0/1, mask rows A/B
-constexpr uint32_t XG_OUT_BYTES = 2 * XG_CHUNK;   // offspring planes 0/1
+constexpr uint32_t XG_ROW = 16 * XG_SPS;           // bytes per row and plane in a stage
+constexpr uint32_t XG_CHUNK = TILE_M * XG_ROW;     // one plane of a stage: 128 rows x 64 B
+constexpr uint32_t XG_IN_BYTES = 4 * XG_CHUNK;     // parent A planes 0/1, parent B planes 0/1
+constexpr uint32_t XG_OUT_BYTES = 2 * XG_CHUNK;    // offspring planes 0/1
+constexpr uint32_t XG_NOROW = 0xFFFFFFFFu;
 
 struct XGBars {
     uint64_t raw_full[XG_R], raw_empty[XG_R];
@@ -67,7 +73,8 @@ struct XGArgs {
     const uint4 *pop;         // [E][n_src][2][W4]
     const int32_t *parents;   // [E][n][2]
     const uint4 *mask;        // [2n][W4]
-    int64_t n_src, n, rows;   // rows = E * n
+    uint4 *out_pop;           // [E][n][2][W4]
+    int64_t n_src, n, E, rows;  // rows = E * n
     int W4;
 };
 
@@ -86,17 +93,23 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
-// smem: input ring [XG_R][6][128][32 B], output ring [XG_OR][2][128][32 B], B stages [XG_S][N/8][8 ki][8][16 B]
+// byte offset of 16-byte quarter q of row t inside a [128 rows][64 B] chunk: quarters XOR-swizzled with the row, so
+// that 8 consecutive rows reading the same quarter hit 8 different 16-byte bank groups
+__device__ __forceinline__ uint32_t swz(int t, int q) { return (uint32_t)t * XG_ROW + (uint32_t)((q ^ ((t >> 1) & 3)) * 16); }
+
+// smem: input ring [XG_R][4][128][64 B], output ring [XG_OR][2][128][64 B], B stages [XG_S][N/8][8 ki][8][16 B]
 __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
-    cross_gebv_kernel(const __grid_constant__ CUtensorMap out_map, const XGArgs fa, const int8_t *__restrict__ bdig, int N, int T,
-                      int steps_total, int steps_per_split, unsigned long long *__restrict__ acc, unsigned int *__restrict__ tile_cnt,
+    cross_gebv_kernel(const XGArgs fa, const int8_t *__restrict__ bdig, int N, int T, int steps_total, int steps_per_split,
+                      unsigned long long *__restrict__ acc, unsigned int *__restrict__ tile_cnt,
                       const double *__restrict__ inv_scale, float *__restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) XGBars bars;
     __shared__ uint32_t tmem_base_slot;
     __shared__ uint32_t last_cta_flag;
-    __shared__ uint32_t row_src[2 * TILE_M], row_msk[2 * TILE_M];  // per (offspring t, parent p): uint4 offsets
+    // per offspring t of the tile: uint4 offsets of its parents' rows (plane 0; plane 1 follows) and mask rows, and
+    // its row index in out_pop / gebv (XG_NOROW past the end)
+    __shared__ uint32_t row_src[2 * TILE_M], row_msk[2 * TILE_M], row_out[TILE_M];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t in_base = smem_u32(smem);
@@ -104,11 +117,9 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
     const uint32_t b_base0 = out_base + XG_OR * XG_OUT_BYTES;
     const uint32_t b_bytes = (uint32_t)N * STEP_K;
     const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
-    const int s_begin = blockIdx.y * steps_per_split;  // even (launcher)
-    const int nst = min(steps_total, s_begin + steps_per_split) - s_begin;
-    // stages hold two steps; an odd tail gets a phantom step past the end of the row: its inputs are zero-filled,
-    // its digit tile is the zero step of slack, its output columns are clipped by the TMA store
-    const int nstages = (nst + 1) >> 1, nst2 = 2 * nstages;
+    const int s_begin = blockIdx.y * steps_per_split;                              // a multiple of XG_SPS (launcher)
+    const int nst = min(steps_total, s_begin + steps_per_split) - s_begin;          // a multiple of XG_SPS too
+    const int nstages = nst / XG_SPS;
 
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
@@ -124,11 +135,11 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
     if (tid == 0) {
         for (int i = 0; i < XG_R; ++i) {
             mbar_init(smem_u32(&bars.raw_full[i]), XG_LOADERS);  // one cp.async completion arrival per loader thread
-            mbar_init(smem_u32(&bars.raw_empty[i]), 8);          // the 8 expander warps (4 per step)
+            mbar_init(smem_u32(&bars.raw_empty[i]), 8);          // the 8 expander warps
         }
         for (int i = 0; i < XG_OR; ++i) {
-            mbar_init(smem_u32(&bars.out_full[i]), 8);
-            mbar_init(smem_u32(&bars.out_empty[i]), 1);  // the storer, once the TMA store has read the stage
+            mbar_init(smem_u32(&bars.out_full[i]), 8);   // the 8 expander warps
+            mbar_init(smem_u32(&bars.out_empty[i]), 1);  // the storer warp
         }
         for (int i = 0; i < XG_S; ++i) {
             mbar_init(smem_u32(&bars.a_full[i]), 4);   // the 4 warps of the group that filled the stage
@@ -138,20 +149,22 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
         mbar_init(smem_u32(&bars.done), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // (offspring t, parent p) of the tile: source row = plane 0 of parent p (plane 1 follows), mask row 2i + p
-    for (int prow = tid; prow < 2 * TILE_M; prow += blockDim.x) {
-        const int64_t gi = row0 + (prow >> 1);
-        uint32_t src = 0xFFFFFFFFu, msk = 0;
-        if (gi < fa.rows) {
-            const int64_t e = gi / fa.n, i = gi % fa.n;
-            int64_t a = fa.parents[gi * 2 + (prow & 1)];
+    for (int k = tid; k < 2 * TILE_M; k += blockDim.x) {
+        const int t = k >> 1, p = k & 1;
+        const int64_t R = row0 + t;
+        uint32_t src = XG_NOROW, msk = 0, orow = XG_NOROW;
+        if (R < fa.rows) {
+            const int64_t i = R / fa.E, e = R % fa.E;  // child-major tile rows
+            orow = (uint32_t)(e * fa.n + i);
+            int64_t a = fa.parents[(int64_t)orow * 2 + p];
             a += a < 0 ? fa.n_src : 0;  // jnp indexing: negatives wrap once, then clamp
             a = a < 0 ? 0 : (a > fa.n_src - 1 ? fa.n_src - 1 : a);
             src = (uint32_t)(((e * fa.n_src + a) * 2) * fa.W4);
-            msk = (uint32_t)((2 * i + (prow & 1)) * fa.W4);
+            msk = (uint32_t)((2 * i + p) * fa.W4);
         }
-        row_src[prow] = src;
-        row_msk[prow] = msk;
+        row_src[k] = src;
+        row_msk[k] = msk;
+        if (p == 0) row_out[t] = orow;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -160,44 +173,50 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
     const uint32_t tmem_a = tmem_d + d_cols;
 
     if (warp < 8) {
-        // ---------------- expanders: group g takes the steps j with j % 2 == g (= half g of every stage) ----------------
+        // ---------------- expanders: group g takes the steps j with j % 2 == g ----------------
         const int g = warp >> 2, r = tid & (TILE_M - 1);
         const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quadrant
-        const uint32_t in_off = (uint32_t)r * 32 + (uint32_t)((g ^ ((r >> 2) & 1)) * 16);  // swizzled half of this row
-        const uint32_t out_off = (uint32_t)r * 32 + (uint32_t)g * 16;                      // dense (TMA box layout)
+        const uint4 *mrow_a = fa.mask + row_msk[2 * r] + s_begin, *mrow_b = fa.mask + row_msk[2 * r + 1] + s_begin;
+        uint4 ma_next = __ldg(mrow_a + g), mb_next = __ldg(mrow_b + g);
         for (int st = 0; st < nstages; ++st) {
-            const int j = 2 * st + g;
-            const int rs = st % XG_R;
+            const int rs = st % XG_R, os = st % XG_OR;
             mbar_wait(smem_u32(&bars.raw_full[rs]), (st / XG_R) & 1);
-            const uint32_t src = in_base + rs * XG_IN_BYTES + in_off;
-            const uint4 a0 = lds128(src), a1 = lds128(src + XG_CHUNK);
-            const uint4 b0 = lds128(src + 2 * XG_CHUNK), b1 = lds128(src + 3 * XG_CHUNK);
-            const uint4 ma = lds128(src + 4 * XG_CHUNK), mb = lds128(src + 5 * XG_CHUNK);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[rs]));
-            const uint4 x0 = blend4(a0, a1, ma), x1 = blend4(b0, b1, mb);
-            // offspring words -> output stage (the storer's TMA store reads it through the async proxy)
-            const int os = st % XG_OR;
             if (st >= XG_OR) mbar_wait(smem_u32(&bars.out_empty[os]), ((st / XG_OR) - 1) & 1);
-            const uint32_t dst = out_base + os * XG_OUT_BYTES + out_off;
-            sts128(dst, x0);
-            sts128(dst + XG_CHUNK, x1);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t in_stage = in_base + rs * XG_IN_BYTES, out_stage = out_base + os * XG_OUT_BYTES;
+#pragma unroll
+            for (int k = 0; k < XG_SPS / 2; ++k) {
+                const int q = 2 * k + g, j = XG_SPS * st + q;  // quarter of the stage row, step of this CTA
+                const uint32_t off = swz(r, q);
+                const uint4 a0 = lds128(in_stage + off), a1 = lds128(in_stage + XG_CHUNK + off);
+                const uint4 b0 = lds128(in_stage + 2 * XG_CHUNK + off), b1 = lds128(in_stage + 3 * XG_CHUNK + off);
+                if (k == XG_SPS / 2 - 1) {  // last read of this input stage: hand it back to the loaders
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[rs]));
+                }
+                const uint4 ma = ma_next, mb = mb_next;
+                if (j + 2 < nst) {  // masks of this thread's next step
+                    ma_next = __ldg(mrow_a + j + 2);
+                    mb_next = __ldg(mrow_b + j + 2);
+                }
+                const uint4 x0 = blend4(a0, a1, ma), x1 = blend4(b0, b1, mb);
+                sts128(out_stage + off, x0);
+                sts128(out_stage + XG_CHUNK + off, x1);
+                // dosage bytes -> tensor memory
+                const DosageFields f = dosage_fields(x0, x1);
+                const int as = j % XG_S;
+                if (j >= XG_S) mbar_wait(smem_u32(&bars.a_empty[as]), ((j / XG_S) - 1) & 1);  // MMAs of the previous use retired
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                dosage_to_tmem(tmem_a + lane_sel + (uint32_t)as * (STEP_K / 4), f);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[as]));
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars.out_full[os]));
-            // dosage bytes -> tensor memory
-            const DosageFields f = dosage_fields(x0, x1);
-            const int as = j % XG_S;
-            if (j >= XG_S) mbar_wait(smem_u32(&bars.a_empty[as]), ((j / XG_S) - 1) & 1);  // MMAs of the previous use retired
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            dosage_to_tmem(tmem_a + lane_sel + (uint32_t)as * (STEP_K / 4), f);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[as]));
         }
     } else if (warp == 8) {
         if (lane == 0) {
             // ---------------- digit tiles (1-D bulk copies) ----------------
-            for (int j = 0; j < nst2; ++j) {
+            for (int j = 0; j < nst; ++j) {
                 const int bs = j % XG_S;
                 if (j >= XG_S) mbar_wait(smem_u32(&bars.a_empty[bs]), ((j / XG_S) - 1) & 1);
                 const uint32_t full = smem_u32(&bars.b_full[bs]);
@@ -212,7 +231,7 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
             const uint32_t idesc = idesc_u8s8(N);
-            for (int j = 0; j < nst2; ++j) {
+            for (int j = 0; j < nst; ++j) {
                 const int as = j % XG_S;
                 const uint32_t par = (j / XG_S) & 1;
                 mbar_wait(smem_u32(&bars.b_full[as]), par);
@@ -227,61 +246,62 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
             mma_commit(smem_u32(&bars.done));
         }
     } else if (warp == 10) {
-        if (lane == 0) {
-            // ---------------- storer: offspring stages -> HBM (TMA store, 3-D map [rows][2 planes][Wpad words]) ----------------
-            const int y = (int)row0;
-            for (int st = 0; st < nstages; ++st) {
-                const int os = st % XG_OR;
-                mbar_wait(smem_u32(&bars.out_full[os]), (st / XG_OR) & 1);
-                const uint32_t src = out_base + os * XG_OUT_BYTES;
-                const int x = (s_begin + 2 * st) * 4;  // word column; columns past Wpad and rows past `rows` are clipped
+        // ---------------- storer: output stages -> HBM; lane covers quarter q of rows (lane >> 2) + 8k ----------------
+        const int q = lane & 3;
+        for (int st = 0; st < nstages; ++st) {
+            const int os = st % XG_OR;
+            mbar_wait(smem_u32(&bars.out_full[os]), (st / XG_OR) & 1);
+            const uint32_t stage = out_base + os * XG_OUT_BYTES;
+            const int w4 = s_begin + XG_SPS * st + q;
+#pragma unroll 2
+            for (int k0 = 0; k0 < TILE_M / 8; k0 += 4) {
+                uint4 v[4][2];
+                uint32_t orow[4];
 #pragma unroll
-                for (int p = 0; p < 2; ++p)
-                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
-                                     reinterpret_cast<uint64_t>(&out_map)),
-                                 "r"(x), "r"(p), "r"(y), "r"(src + p * XG_CHUNK)
-                                 : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (st >= 1) {  // the previous store has read its stage: hand it back
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    mbar_arrive(smem_u32(&bars.out_empty[(st - 1) % XG_OR]));
+                for (int k = 0; k < 4; ++k) {
+                    const int t = (lane >> 2) + 8 * (k0 + k);
+                    orow[k] = row_out[t];
+                    v[k][0] = lds128(stage + swz(t, q));
+                    v[k][1] = lds128(stage + XG_CHUNK + swz(t, q));
                 }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (orow[k] != XG_NOROW) {
+                        uint4 *dst = fa.out_pop + (int64_t)orow[k] * 2 * fa.W4 + w4;
+                        dst[0] = v[k][0];
+                        dst[fa.W4] = v[k][1];
+                    }
             }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all offspring bytes written before the CTA retires
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars.out_empty[os]));
         }
     } else {
-        // ---------------- loaders: thread u covers half h = u & 1 of rows u >> 1 and 64 + (u >> 1), all 6 chunks ----------------
-        const int u = tid - XG_LOADER_WARP0 * 32, h = u & 1;
-        uint32_t src[2][2], msk[2][2], dst[2];
-        bool valid[2];
+        // ---------------- loaders: thread u covers quarter q = u & 3 of rows (u >> 2) + 32k, both planes of both parents ----------------
+        const int u = tid - XG_LOADER_WARP0 * 32, q = u & 3;
+        uint32_t src[4][2], dst[4];
+        uint32_t valid = 0;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int t = (u >> 1) + 64 * k;
+        for (int k = 0; k < 4; ++k) {
+            const int t = (u >> 2) + 32 * k;
             src[k][0] = row_src[2 * t];
             src[k][1] = row_src[2 * t + 1];
-            msk[k][0] = row_msk[2 * t];
-            msk[k][1] = row_msk[2 * t + 1];
-            valid[k] = src[k][0] != 0xFFFFFFFFu;
-            if (!valid[k]) src[k][0] = src[k][1] = 0;
-            dst[k] = (uint32_t)t * 32 + (uint32_t)((h ^ ((t >> 2) & 1)) * 16);
+            if (src[k][0] != XG_NOROW) valid |= 1u << k;
+            else src[k][0] = src[k][1] = 0;
+            dst[k] = swz(t, q);
         }
         for (int st = 0; st < nstages; ++st) {
             const int rs = st % XG_R;
             if (st >= XG_R) mbar_wait(smem_u32(&bars.raw_empty[rs]), ((st / XG_R) - 1) & 1);
-            const int w4 = s_begin + 2 * st + h;
-            const bool in_row = w4 < fa.W4;
-            const int w4c = in_row ? w4 : 0;
+            const int w4 = s_begin + XG_SPS * st + q;
             const uint32_t stage = in_base + rs * XG_IN_BYTES;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint32_t nbytes = (in_row && valid[k]) ? 16u : 0u;  // 0: zero-fill, nothing is read
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t nbytes = ((valid >> k) & 1) ? 16u : 0u;  // 0: zero-fill, nothing is read
                 const uint32_t d = stage + dst[k];
-                cp_async16(d, fa.pop + src[k][0] + w4c, nbytes);
-                cp_async16(d + XG_CHUNK, fa.pop + src[k][0] + fa.W4 + w4c, nbytes);
-                cp_async16(d + 2 * XG_CHUNK, fa.pop + src[k][1] + w4c, nbytes);
-                cp_async16(d + 3 * XG_CHUNK, fa.pop + src[k][1] + fa.W4 + w4c, nbytes);
-                cp_async16(d + 4 * XG_CHUNK, fa.mask + msk[k][0] + w4c, nbytes);
-                cp_async16(d + 5 * XG_CHUNK, fa.mask + msk[k][1] + w4c, nbytes);
+                cp_async16(d, fa.pop + src[k][0] + w4, nbytes);
+                cp_async16(d + XG_CHUNK, fa.pop + src[k][0] + fa.W4 + w4, nbytes);
+                cp_async16(d + 2 * XG_CHUNK, fa.pop + src[k][1] + w4, nbytes);
+                cp_async16(d + 3 * XG_CHUNK, fa.pop + src[k][1] + fa.W4 + w4, nbytes);
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars.raw_full[rs])) : "memory");
         }
@@ -290,7 +310,8 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
 
     if (warp < 4) {
         mbar_wait(smem_u32(&bars.done), 0);
-        digits_epilogue(tmem_d, tid, warp, row0, fa.rows, T, acc, tile_cnt, inv_scale, out, &last_cta_flag, blockIdx.x, gridDim.y);
+        digits_epilogue(tmem_d, tid, warp, row0, fa.rows, T, acc, tile_cnt, inv_scale, out, &last_cta_flag, blockIdx.x, gridDim.y,
+                        row_out);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -301,7 +322,7 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
 }  // namespace
 
 int bg_tc_reserve_scratch(bg_engine *eng, int scratch, int64_t total, int64_t tiles, cudaStream_t st);
-void bg_tc_split(int64_t tiles, int steps, int64_t target, bool even, int *ksplit_out, int *sps_out);
+void bg_tc_split(int64_t tiles, int steps, int64_t target, int multiple, int *ksplit_out, int *sps_out);
 
 // vector-env step: out_pop[e][i] = cross of pop[e][parents[e][i][0..1]] under mask[2i..2i+1]; gebv[e][i][T]
 int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
@@ -309,25 +330,13 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
 {
     BG_REQUIRE(eng && eng->d_wdig, BG_ESTATE, "engine has no tensor-core digit table");
     const int T = eng->T, N = eng->tc_N;
-    const int steps = (int)eng->tc_steps;
+    const int steps = (int)eng->tc_steps;  // a multiple of 8: rows are padded to 32 words
     const int64_t rows = E * n;
     const int64_t tiles = (rows + TILE_M - 1) / TILE_M;
+    BG_REQUIRE(steps % XG_SPS == 0, BG_ESTATE, "row pitch is not a multiple of the fused kernel's stage");
     BG_REQUIRE(tiles < (int64_t(1) << 31) && rows < (int64_t(1) << 31), BG_ELIMIT, "too many rows");
     BG_REQUIRE((int64_t)eng->Wpad / 4 * 2 * (n_src > n ? n_src : n) * E < (int64_t(1) << 32), BG_ELIMIT,
                "population too large for the fused kernel's 32-bit row offsets");
-
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    EncodeTiledFn enc = encode_tiled();
-    BG_REQUIRE(enc, BG_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    // 3-D view of the offspring: [rows][2 planes][Wpad words]; box = 8 words (two steps) x 1 plane x 128 rows
-    const cuuint64_t gdim[3] = {(cuuint64_t)eng->Wpad, 2, (cuuint64_t)rows};
-    const cuuint64_t gstride[2] = {(cuuint64_t)eng->Wpad * 4, (cuuint64_t)eng->Wpad * 8};
-    const cuuint32_t box[3] = {8, 1, TILE_M};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, out_pop, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    BG_REQUIRE(cr == CUDA_SUCCESS, BG_ECUDA, "cuTensorMapEncodeTiled failed (offspring store map)");
 
     const size_t smem = (size_t)XG_R * XG_IN_BYTES + (size_t)XG_OR * XG_OUT_BYTES + (size_t)XG_S * N * STEP_K;
     BG_REQUIRE(smem <= (size_t)eng->max_smem_optin, BG_ELIMIT, "too many traits for the fused cross+GEBV tile");
@@ -341,7 +350,7 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
     if (resident > XG_CTAS) resident = XG_CTAS;
     if (resident < 1) resident = 1;
     int ksplit, sps;
-    bg_tc_split(tiles, steps, 2LL * resident * eng->sm_count /* two waves */, true, &ksplit, &sps);
+    bg_tc_split(tiles, steps, 2LL * resident * eng->sm_count /* two waves */, XG_SPS, &ksplit, &sps);
     int rc = bg_tc_reserve_scratch(eng, 0, rows * T, tiles, st);
     if (rc) return rc;
     if (smem > eng->tc2_optin[1]) {
@@ -352,12 +361,14 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
     fa.pop = reinterpret_cast<const uint4 *>(pop);
     fa.parents = parents;
     fa.mask = reinterpret_cast<const uint4 *>(mask);
+    fa.out_pop = reinterpret_cast<uint4 *>(out_pop);
     fa.n_src = n_src;
     fa.n = n;
+    fa.E = E;
     fa.rows = rows;
     fa.W4 = eng->Wpad / 4;
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
-    cross_gebv_kernel<<<grid, XG_THREADS, smem, st>>>(tmap, fa, eng->d_wdig, N, T, steps, sps, eng->d_acc2[0], eng->d_tile_cnt[0],
+    cross_gebv_kernel<<<grid, XG_THREADS, smem, st>>>(fa, eng->d_wdig, N, T, steps, sps, eng->d_acc2[0], eng->d_tile_cnt[0],
                                                       eng->d_inv_scale, gebv_out);
     BG_LAUNCHED();
     return BG_OK;

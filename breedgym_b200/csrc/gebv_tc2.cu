@@ -207,8 +207,8 @@ int bg_tc_reserve_scratch(bg_engine *eng, int scratch, int64_t total, int64_t ti
     return BG_OK;
 }
 
-// K split: about `target` CTAs, >= 8 steps each, <= 3000 steps each, `even` -> an even number of steps per split
-void bg_tc_split(int64_t tiles, int steps, int64_t target, bool even, int *ksplit_out, int *sps_out)
+// K split: about `target` CTAs, >= 8 steps each, <= 3000 steps each, a multiple of `multiple` steps per split
+void bg_tc_split(int64_t tiles, int steps, int64_t target, int multiple, int *ksplit_out, int *sps_out)
 {
     if (const char *s = getenv("BG_TC_TARGET_CTAS")) target = atoll(s) > 0 ? atoll(s) : target;
     int ksplit = (int)(target / tiles);
@@ -220,7 +220,7 @@ void bg_tc_split(int64_t tiles, int steps, int64_t target, bool even, int *kspli
     if (ksplit < (steps + 2999) / 3000) ksplit = (steps + 2999) / 3000;
     if (ksplit > 65535) ksplit = 65535;
     int sps = (steps + ksplit - 1) / ksplit;
-    if (even) sps += sps & 1;
+    sps = (sps + multiple - 1) / multiple * multiple;
     *ksplit_out = (steps + sps - 1) / sps;
     *sps_out = sps;
 }
@@ -261,7 +261,7 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
     if (resident > 4) resident = 4;  // __launch_bounds__
     if (resident < 1) resident = 1;
     int ksplit, sps;
-    bg_tc_split(tiles, steps, (int64_t)resident * eng->sm_count /* one full wave */, false, &ksplit, &sps);
+    bg_tc_split(tiles, steps, (int64_t)resident * eng->sm_count /* one full wave */, 1, &ksplit, &sps);
     int rc = bg_tc_reserve_scratch(eng, scratch, rows * T, tiles, st);
     if (rc) return rc;
     dim3 grid((unsigned)tiles, (unsigned)ksplit);

@@ -126,10 +126,12 @@ __device__ __forceinline__ void mma_commit(uint32_t bar)
 __device__ __forceinline__ void digits_epilogue(uint32_t tmem_d, int tid, int warp, int64_t row0, int64_t rows, int T,
                                                 unsigned long long *__restrict__ acc, unsigned int *__restrict__ tile_cnt,
                                                 const double *__restrict__ inv_scale, float *__restrict__ out,
-                                                uint32_t *last_cta_flag, unsigned tile_idx, unsigned nsplit)
+                                                uint32_t *last_cta_flag, unsigned tile_idx, unsigned nsplit,
+                                                const uint32_t *out_row_map = nullptr)
 {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t row = row0 + tid;
+    const int64_t row = row0 + tid;  // accumulator slot; the result goes to row `orow` of `out`
+    const int64_t orow = out_row_map ? (int64_t)out_row_map[tid] : row;
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
     const bool single = nsplit == 1;  // no K split: this CTA holds the whole sum
     for (int t = 0; t < T; ++t) {
@@ -145,7 +147,7 @@ __device__ __forceinline__ void digits_epilogue(uint32_t tmem_d, int tid, int wa
         sum = (unsigned long long)((long long)sum >> 6);  // prescaled operand: every (partial) sum is exactly 64x
         if (row < rows) {
             if (single)
-                out[row * T + t] = (float)((double)(long long)sum * inv_scale[t]);
+                out[orow * T + t] = (float)((double)(long long)sum * inv_scale[t]);
             else
                 atomicAdd(acc + row * T + t, sum);  // integer partial sums: order independent
         }
@@ -160,7 +162,7 @@ __device__ __forceinline__ void digits_epilogue(uint32_t tmem_d, int tid, int wa
             if (row < rows)
                 for (int t = 0; t < T; ++t) {
                     const unsigned long long tot = atomicExch(acc + row * T + t, 0ull);
-                    out[row * T + t] = (float)((double)(long long)tot * inv_scale[t]);
+                    out[orow * T + t] = (float)((double)(long long)tot * inv_scale[t]);
                 }
             if (tid == 0) tile_cnt[tile_idx] = 0u;
         }
