@@ -11,7 +11,7 @@
 // multiple of 32 all lanes of a warp read the SAME mask words: one broadcast L1/L2 access per warp instead of a
 // third of the kernel's gather traffic.  Warp roles:
 //
-//   warps 11-14 (loaders)   : cp.async (LDGSTS) 16-byte copies, four lanes per 64-byte row segment: the two bit
+//   warps 10-13 (loaders)   : cp.async (LDGSTS) 16-byte copies, four lanes per 64-byte row segment: the two bit
 //                             planes of parent A and of parent B of every offspring -> a ring of stages
 //                             [4 chunks][128 rows][64 B = 4 steps] in shared memory (16-byte quarters XOR-swizzled
 //                             with the row, so the one-row-per-lane reads below are conflict free).  Nothing
@@ -23,7 +23,8 @@
 //                             with ld.global.nc), one LOP3 per word selects the alleles (h0 & ~M | h1 & M), the
 //                             offspring words go to an output stage in shared memory, then 4 words per plane ->
 //                             128 prescaled dosage bytes -> tcgen05.st into the A stage in tensor memory.
-//   warp 10    (storer)     : output stage -> HBM, four lanes per 64-byte row segment (coalesced 128-bit stores).
+//                             The same warps drain the output stages to HBM, four lanes per 64-byte row segment
+//                             (a single storer warp was the bottleneck: 47 us).
 //   warp 8     (digits)     : 1-D bulk copies (TMA) of the digit tiles.
 //   warp 9     (MMA)        : tcgen05.mma.kind::i8, A from TMEM, B from shared memory, D in TMEM.
 //   warps 0-3  (epilogue)   : digits -> int64 -> K-split atomics -> float32 (tc_common.cuh).
@@ -49,12 +50,19 @@ namespace {
 #ifndef XG_CTAS_VAL
 #define XG_CTAS_VAL 2
 #endif
+#ifndef XG_L2HINT_VAL
+#define XG_L2HINT_VAL 0     // L2 prefetch size hint of the cp.async gathers (0 / 128 / 256 bytes)
+#endif
+#ifndef XG_PREFETCH_VAL
+#define XG_PREFETCH_VAL 0   // 1: bulk L2 prefetch of this CTA's whole K range of every parent row in the prologue
+#endif
 constexpr int XG_R = XG_R_VAL;        // input ring (stages of 4 steps)
-constexpr int XG_S = XG_S_VAL;        // A (TMEM) / B (smem) stages (steps)
+constexpr int XG_S = XG_S_VAL;        // A (TMEM) / B (smem) stages (steps); a separate, deeper digit ring with its own
+                                      // tcgen05.commit per step measured slower (51.2 vs 47.0 us at C2)
 constexpr int XG_OR = XG_OR_VAL;      // output ring (stages of 4 steps)
 constexpr int XG_CTAS = XG_CTAS_VAL;  // CTAs per SM
 constexpr int XG_SPS = 4;             // steps per stage: 64 B per row and plane
-constexpr int XG_LOADER_WARP0 = 11, XG_LOADERS = 128;
+constexpr int XG_LOADER_WARP0 = 10, XG_LOADERS = 128;
 constexpr int XG_THREADS = (XG_LOADER_WARP0 + 4) * 32;
 constexpr uint32_t XG_ROW = 16 * XG_SPS;           // bytes per row and plane in a stage
 constexpr uint32_t XG_CHUNK = TILE_M * XG_ROW;     // one plane of a stage: 128 rows x 64 B
@@ -90,7 +98,13 @@ __device__ __forceinline__ uint4 blend4(const uint4 h0, const uint4 h1, const ui
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes)
 {
+#if XG_L2HINT_VAL == 256
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+#elif XG_L2HINT_VAL == 128
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+#endif
 }
 
 // byte offset of 16-byte quarter q of row t inside a [128 rows][64 B] chunk: quarters XOR-swizzled with the row, so
@@ -139,7 +153,7 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
         }
         for (int i = 0; i < XG_OR; ++i) {
             mbar_init(smem_u32(&bars.out_full[i]), 8);   // the 8 expander warps
-            mbar_init(smem_u32(&bars.out_empty[i]), 1);  // the storer warp
+            mbar_init(smem_u32(&bars.out_empty[i]), 4);  // the 4 loader / storer warps
         }
         for (int i = 0; i < XG_S; ++i) {
             mbar_init(smem_u32(&bars.a_full[i]), 4);   // the 4 warps of the group that filled the stage
@@ -245,65 +259,77 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
             }
             mma_commit(smem_u32(&bars.done));
         }
-    } else if (warp == 10) {
-        // ---------------- storer: output stages -> HBM; lane covers quarter q of rows (lane >> 2) + 8k ----------------
-        const int q = lane & 3;
-        for (int st = 0; st < nstages; ++st) {
-            const int os = st % XG_OR;
-            mbar_wait(smem_u32(&bars.out_full[os]), (st / XG_OR) & 1);
-            const uint32_t stage = out_base + os * XG_OUT_BYTES;
-            const int w4 = s_begin + XG_SPS * st + q;
-#pragma unroll 2
-            for (int k0 = 0; k0 < TILE_M / 8; k0 += 4) {
-                uint4 v[4][2];
-                uint32_t orow[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int t = (lane >> 2) + 8 * (k0 + k);
-                    orow[k] = row_out[t];
-                    v[k][0] = lds128(stage + swz(t, q));
-                    v[k][1] = lds128(stage + XG_CHUNK + swz(t, q));
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (orow[k] != XG_NOROW) {
-                        uint4 *dst = fa.out_pop + (int64_t)orow[k] * 2 * fa.W4 + w4;
-                        dst[0] = v[k][0];
-                        dst[fa.W4] = v[k][1];
-                    }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars.out_empty[os]));
-        }
     } else {
-        // ---------------- loaders: thread u covers quarter q = u & 3 of rows (u >> 2) + 32k, both planes of both parents ----------------
+        // ---------------- loaders / storers: thread u covers quarter q = u & 3 of rows (u >> 2) + 32k ----------------
+        // per iteration: gather stage `it` (both planes of both parents, 16 cp.async in flight, no register staging),
+        // then drain the offspring stage the expanders finished XG_R stages earlier (coalesced 128-bit stores)
         const int u = tid - XG_LOADER_WARP0 * 32, q = u & 3;
-        uint32_t src[4][2], dst[4];
+        uint32_t src[4][2], dst[4], orow[4];
         uint32_t valid = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int t = (u >> 2) + 32 * k;
             src[k][0] = row_src[2 * t];
             src[k][1] = row_src[2 * t + 1];
+            orow[k] = row_out[t];
             if (src[k][0] != XG_NOROW) valid |= 1u << k;
             else src[k][0] = src[k][1] = 0;
             dst[k] = swz(t, q);
         }
-        for (int st = 0; st < nstages; ++st) {
-            const int rs = st % XG_R;
-            if (st >= XG_R) mbar_wait(smem_u32(&bars.raw_empty[rs]), ((st / XG_R) - 1) & 1);
-            const int w4 = s_begin + XG_SPS * st + q;
-            const uint32_t stage = in_base + rs * XG_IN_BYTES;
+#if XG_PREFETCH_VAL
+        if (q == 0) {
+            // whole K range of this CTA, one request per row and plane (measured slower at C2: 51.6 vs 47.0 us)
+            const uint32_t pbytes = (uint32_t)nst * 16;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t nbytes = ((valid >> k) & 1) ? 16u : 0u;  // 0: zero-fill, nothing is read
-                const uint32_t d = stage + dst[k];
-                cp_async16(d, fa.pop + src[k][0] + w4, nbytes);
-                cp_async16(d + XG_CHUNK, fa.pop + src[k][0] + fa.W4 + w4, nbytes);
-                cp_async16(d + 2 * XG_CHUNK, fa.pop + src[k][1] + w4, nbytes);
-                cp_async16(d + 3 * XG_CHUNK, fa.pop + src[k][1] + fa.W4 + w4, nbytes);
+            for (int k = 0; k < 4; ++k)
+                if ((valid >> k) & 1) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 *a = fa.pop + src[k][c >> 1] + (c & 1) * fa.W4 + s_begin;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(pbytes) : "memory");
+                    }
+                }
+        }
+#endif
+        for (int it = 0; it < nstages + XG_R; ++it) {
+            if (it < nstages) {
+                const int rs = it % XG_R;
+                if (it >= XG_R) mbar_wait(smem_u32(&bars.raw_empty[rs]), ((it / XG_R) - 1) & 1);
+                const int w4 = s_begin + XG_SPS * it + q;
+                const uint32_t stage = in_base + rs * XG_IN_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t nbytes = ((valid >> k) & 1) ? 16u : 0u;  // 0: zero-fill, nothing is read
+                    const uint32_t d = stage + dst[k];
+                    cp_async16(d, fa.pop + src[k][0] + w4, nbytes);
+                    cp_async16(d + XG_CHUNK, fa.pop + src[k][0] + fa.W4 + w4, nbytes);
+                    cp_async16(d + 2 * XG_CHUNK, fa.pop + src[k][1] + w4, nbytes);
+                    cp_async16(d + 3 * XG_CHUNK, fa.pop + src[k][1] + fa.W4 + w4, nbytes);
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars.raw_full[rs])) : "memory");
             }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars.raw_full[rs])) : "memory");
+            const int so = it - XG_R;
+            if (so >= 0) {
+                const int os = so % XG_OR;
+                mbar_wait(smem_u32(&bars.out_full[os]), (so / XG_OR) & 1);
+                const uint32_t stage = out_base + os * XG_OUT_BYTES;
+                const int w4 = s_begin + XG_SPS * so + q;
+                uint4 v[4][2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[k][0] = lds128(stage + dst[k]);
+                    v[k][1] = lds128(stage + XG_CHUNK + dst[k]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars.out_empty[os]));  // the stage is in registers
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (orow[k] != XG_NOROW) {
+                        uint4 *o = fa.out_pop + (int64_t)orow[k] * 2 * fa.W4 + w4;
+                        o[0] = v[k][0];
+                        o[fa.W4] = v[k][1];
+                    }
+            }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     }

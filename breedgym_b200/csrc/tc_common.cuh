@@ -35,17 +35,30 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+#ifndef BG_MBAR_HINT_NS
+#define BG_MBAR_HINT_NS 2000   // suspend-time hint of mbarrier.try_wait (0: plain try_wait spin)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
+#if BG_MBAR_HINT_NS > 0
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"  // sleeps up to %3 ns unless the phase completes
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(2000u)
+            : "r"(bar), "r"(parity), "r"((uint32_t)BG_MBAR_HINT_NS)
             : "memory");
+#else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+#endif
         if (spin > SPIN_LIMIT) __trap();
     }
 }
