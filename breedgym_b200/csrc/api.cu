@@ -422,14 +422,14 @@ static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *p
                            int64_t n, const uint32_t cross_key[2], const uint32_t *next_key, int layout, int schedule,
                            float *gebv_out, cudaStream_t st)
 {
-    // The single-kernel cross+GEBV (row-per-lane parent loads) measured slower than blend + TMA-fed GEBV at
-    // C2 (94-110 vs 72-85 us per step): it stays selectable (BG_FUSE=1) but is not the default path.
-    const bool no_fuse = getenv("BG_FUSE") == nullptr;
+    // One fused cross+GEBV kernel (cross_gebv.cu: 47 us at C2 against 33 + 32 us for blend + GEBV) whenever the
+    // tensor-core path applies; BG_NO_FUSE=1 selects the two-kernel path (cross-checks, tuning).
+    const bool no_fuse = getenv("BG_NO_FUSE") != nullptr;
     int slot = 0;
     int rc = masks_acquire(eng, cross_key, layout, schedule, 2 * n, st, &slot);
     if (rc) return rc;
     const bg_mask_slot &sl = eng->slots[slot];
-    if (gebv_out && eng->tc_N && !eng->mut_thr && !no_fuse) {
+    if (gebv_out && !no_fuse && bg_cross_gebv_fused_ok(eng, E, n_src, n)) {
         rc = bg_launch_cross_gebv_fused(eng, pop, parents, sl.mask, out, E, n_src, n, gebv_out, st);
     } else if (gebv_out && eng->tc_N && E >= 16 && getenv("BG_SPLIT") != nullptr) {
         // Opt-in experiment: two halves of the env batch, software-pipelined over two streams -- the GEBV of the first

@@ -99,6 +99,7 @@ int bg_gebv_tc_max_traits(void);
 int bg_launch_gebv_tc(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st);
 // gebv_tc2.cu: TMA tile loads + operand A in tensor memory
 int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st, int scratch = 0);
+bool bg_cross_gebv_fused_ok(const bg_engine *eng, int64_t E, int64_t n_src, int64_t n);
 int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
                                int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st);
 

@@ -350,6 +350,19 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
 int bg_tc_reserve_scratch(bg_engine *eng, int scratch, int64_t total, int64_t tiles, cudaStream_t st);
 void bg_tc_split(int64_t tiles, int steps, int64_t target, int multiple, int *ksplit_out, int *sps_out);
 
+// can the fused kernel take this engine's trait count and this population size?  (else: blend + GEBV kernels)
+bool bg_cross_gebv_fused_ok(const bg_engine *eng, int64_t E, int64_t n_src, int64_t n)
+{
+    if (!eng || !eng->d_wdig || eng->mut_thr) return false;
+    const int N = eng->tc_N;
+    const size_t smem = (size_t)XG_R * XG_IN_BYTES + (size_t)XG_OR * XG_OUT_BYTES + (size_t)XG_S * N * STEP_K;
+    uint32_t d_cols = 32;
+    while ((int)d_cols < N) d_cols <<= 1;
+    if (smem > (size_t)eng->max_smem_optin || d_cols + XG_S * (STEP_K / 4) > 512) return false;
+    if (eng->tc_steps % XG_SPS != 0 || E * n >= (int64_t(1) << 31)) return false;
+    return (int64_t)eng->Wpad / 4 * 2 * (n_src > n ? n_src : n) * E < (int64_t(1) << 32);
+}
+
 // vector-env step: out_pop[e][i] = cross of pop[e][parents[e][i][0..1]] under mask[2i..2i+1]; gebv[e][i][T]
 int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
                                int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st)

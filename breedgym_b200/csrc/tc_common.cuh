@@ -128,6 +128,25 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t a_taddr, uin
         "r"(a_taddr), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// warp-uniform variants: called by ALL lanes of a converged warp with identical arguments, one elected lane issues.
+// (Issuing from inside an `if (lane == 0)` region makes ptxas wrap every UTCIMMA in an ELECT / BRA.U.ANY loop and
+// re-derive its uniform-register operands: ~100 cycles per MMA, 700 per 128-marker step.)
+__device__ __forceinline__ void mma_i8_ts_warp(uint32_t tmem_d, uint32_t a_taddr, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_taddr), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_warp(uint32_t bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

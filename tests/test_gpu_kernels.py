@@ -418,7 +418,9 @@ def test_full_size_vector_step_sampled_rows_and_properties(cuda_device):
         assert np.allclose(gebv[e], cr.gebv(got[e], sim.GEBV_model.marker_effects), rtol=GEBV_RTOL, atol=0)
 
 
-@pytest.mark.parametrize("m,T,E,n_src,n", [(10000, 1, 5, 37, 41), (333, 3, 3, 20, 130), (100002, 1, 2, 9, 7), (4099, 16, 4, 12, 64)])
+@pytest.mark.parametrize("m,T,E,n_src,n", [(10000, 1, 5, 37, 41), (333, 3, 3, 20, 130), (100002, 1, 2, 9, 7), (4099, 16, 4, 12, 64),
+                                           (10000, 1, 64, 20, 25), (1000, 2, 32, 10, 13), (777, 1, 40, 7, 9), (2049, 1, 128, 5, 3),
+                                           (4097, 4, 17, 6, 33)])
 def test_fused_cross_gebv_equals_cross_then_gebv(cuda_device, m, T, E, n_src, n):
     """bg_cross_gebv (one fused kernel for E > 1) == bg_cross followed by bg_gebv, bit for bit, and == the oracle."""
     import torch
@@ -439,12 +441,19 @@ def test_fused_cross_gebv_equals_cross_then_gebv(cuda_device, m, T, E, n_src, n)
     a = torch.from_numpy(acts).to(cuda_device)
     import os
 
-    os.environ["BG_FUSE"] = "1"  # read by the library on every call: exercises the single-kernel path
-    _lib.check(_lib.load().bg_cross_gebv(sim._engine, packed.words.data_ptr(), a.data_ptr(), out.data_ptr(), E, n_src, n,
-                                         _lib.nptr(key), sim._layout(), sim._schedule(), gebv.data_ptr(), sim._stream()))
-    os.environ.pop("BG_FUSE")
-    assert np.array_equal(out.cpu().numpy(), ref_pop.words.cpu().numpy())
-    assert np.array_equal(gebv.cpu().numpy(), ref_gebv)
+    # default: the single fused kernel; BG_NO_FUSE=1 (read by the library on every call): blend + GEBV kernels
+    for no_fuse in (False, True):
+        out.zero_()
+        gebv.zero_()
+        if no_fuse:
+            os.environ["BG_NO_FUSE"] = "1"
+        try:
+            _lib.check(_lib.load().bg_cross_gebv(sim._engine, packed.words.data_ptr(), a.data_ptr(), out.data_ptr(), E, n_src, n,
+                                                 _lib.nptr(key), sim._layout(), sim._schedule(), gebv.data_ptr(), sim._stream()))
+        finally:
+            os.environ.pop("BG_NO_FUSE", None)
+        assert np.array_equal(out.cpu().numpy(), ref_pop.words.cpu().numpy())
+        assert np.array_equal(gebv.cpu().numpy(), ref_gebv)
     oref = co.cross_envs(pops, cr.normalize_index(acts, n_src), sim.recombination_vec, key)
     from breedgym_b200.population import PackedPopulation
 
