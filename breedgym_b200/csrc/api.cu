@@ -407,12 +407,17 @@ static int masks_release(bg_engine *eng, int slot, cudaStream_t st)
 }
 
 // start generating the masks of the NEXT cross key on the side stream (other slot than `cur`)
-static int masks_lookahead(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, int cur)
+// `after_step`: start only once the kernels of the current step are done (their `freed` record).  The host-facing
+// step synchronises and leaves the GPU idle while the host works: the integer-bound mask kernel then runs in that gap
+// instead of competing with the step kernel for issue slots.  The device-resident pipeline has no gap: there the two
+// overlap.
+static int masks_lookahead(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, int cur, bool after_step)
 {
     for (int i = 0; i < 2; ++i)
         if (slot_matches(eng->slots[i], key, layout, schedule, rows)) return BG_OK;
     if (!eng->side) BG_CUDA(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
     bg_mask_slot &sl = eng->slots[cur ^ 1];
+    if (after_step && eng->slots[cur].freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, eng->slots[cur].freed, 0));
     if (sl.freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, sl.freed, 0));  // its last reader (an earlier blend) is done
     return slot_generate(eng, sl, key, layout, schedule, rows, eng->side);
 }
@@ -420,7 +425,7 @@ static int masks_lookahead(bg_engine *eng, const uint32_t key[2], int layout, in
 // gebv_out != nullptr: also score the offspring; fused into one kernel when the tensor-core path applies
 static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src,
                            int64_t n, const uint32_t cross_key[2], const uint32_t *next_key, int layout, int schedule,
-                           float *gebv_out, cudaStream_t st)
+                           float *gebv_out, cudaStream_t st, bool lookahead_after_step = false)
 {
     // One fused cross+GEBV kernel (cross_gebv.cu: 47 us at C2 against 33 + 32 us for blend + GEBV) whenever the
     // tensor-core path applies; BG_NO_FUSE=1 selects the two-kernel path (cross-checks, tuning).
@@ -465,7 +470,7 @@ static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *p
     rc = masks_release(eng, slot, st);
     if (rc) return rc;
     static const bool no_lookahead = getenv("BG_NO_LOOKAHEAD") != nullptr;  // diagnostics
-    if (next_key && !no_lookahead) rc = masks_lookahead(eng, next_key, layout, schedule, 2 * n, slot);
+    if (next_key && !no_lookahead) rc = masks_lookahead(eng, next_key, layout, schedule, 2 * n, slot, lookahead_after_step);
     return rc;
 }
 
@@ -640,7 +645,8 @@ int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_
                                     n_src, 0, out, st);
         if (!rc) rc = bg_launch_gebv(eng, out, n, gebv_dev, 0, st);
     } else {
-        rc = cross_envs_impl(eng, pop, actions_dev, out, E, n_src, n, cross_key, next_cross_key, layout, schedule, gebv_dev, st);
+        rc = cross_envs_impl(eng, pop, actions_dev, out, E, n_src, n, cross_key, next_cross_key, layout, schedule, gebv_dev, st,
+                             gebv_host != nullptr || reward_host != nullptr);
     }
     if (rc) return rc;
     tm.lap(1);

@@ -242,23 +242,23 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
             }
         }
     } else if (warp == 9) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
-            const uint32_t idesc = idesc_u8s8(N);
-            for (int j = 0; j < nst; ++j) {
-                const int as = j % XG_S;
-                const uint32_t par = (j / XG_S) & 1;
-                mbar_wait(smem_u32(&bars.b_full[as]), par);
-                mbar_wait(smem_u32(&bars.a_full[as]), par);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues ----------------
+        const uint32_t idesc = idesc_u8s8(N);
+        for (int j = 0; j < nst; ++j) {
+            const int as = j % XG_S;
+            const uint32_t par = (j / XG_S) & 1;
+            const uint32_t a_taddr = tmem_a + (uint32_t)as * (STEP_K / 4);
+            const uint64_t bdesc = make_smem_desc(b_base0 + as * b_bytes, 128, 1024);
+            mbar_wait(smem_u32(&bars.b_full[as]), par);
+            mbar_wait(smem_u32(&bars.a_full[as]), par);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            __syncwarp();
 #pragma unroll
-                for (int kk = 0; kk < STEP_K / 32; ++kk)
-                    mma_i8_ts(tmem_d, tmem_a + (uint32_t)as * (STEP_K / 4) + 8 * kk,
-                              make_smem_desc(b_base0 + as * b_bytes + kk * 256, 128, 1024), idesc, (j > 0 || kk > 0) ? 1u : 0u);
-                mma_commit(smem_u32(&bars.a_empty[as]));
-            }
-            mma_commit(smem_u32(&bars.done));
+            for (int kk = 0; kk < STEP_K / 32; ++kk)  // +16 in the descriptor's address field = +256 bytes
+                mma_i8_ts_warp(tmem_d, a_taddr + 8 * kk, bdesc + 16 * kk, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+            mma_commit_warp(smem_u32(&bars.a_empty[as]));
         }
+        mma_commit_warp(smem_u32(&bars.done));
     } else {
         // ---------------- loaders / storers: thread u covers quarter q = u & 3 of rows (u >> 2) + 32k ----------------
         // per iteration: gather stage `it` (both planes of both parents, 16 cp.async in flight, no register staging),

@@ -155,22 +155,24 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
                              : "memory");
             }
         }
-    } else if (warp == 9 && lane == 0) {
-        // ---------------- MMA issuer ----------------
+    } else if (warp == 9) {
+        // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues ----------------
         const uint32_t idesc = idesc_u8s8(N);
         for (int j = 0; j < nst; ++j) {
             const int as = j % T2_S;
             const uint32_t par = (j / T2_S) & 1;
+            const uint32_t a_taddr = tmem_a + (uint32_t)as * (T2_KS / 4);
+            const uint64_t bdesc = make_smem_desc(b_base0 + as * b_bytes, 128, 1024);
             mbar_wait(smem_u32(&bars.b_full[as]), par);
             mbar_wait(smem_u32(&bars.a_full[as]), par);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            __syncwarp();
 #pragma unroll
-            for (int kk = 0; kk < T2_KS / 32; ++kk)
-                mma_i8_ts(tmem_d, tmem_a + (uint32_t)as * (T2_KS / 4) + 8 * kk, make_smem_desc(b_base0 + as * b_bytes + kk * 256, 128, 1024),
-                          idesc, (j > 0 || kk > 0) ? 1u : 0u);
-            mma_commit(smem_u32(&bars.a_empty[as]));
+            for (int kk = 0; kk < T2_KS / 32; ++kk)  // +16 in the descriptor's address field = +256 bytes
+                mma_i8_ts_warp(tmem_d, a_taddr + 8 * kk, bdesc + 16 * kk, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+            mma_commit_warp(smem_u32(&bars.a_empty[as]));
         }
-        mma_commit(smem_u32(&bars.done));
+        mma_commit_warp(smem_u32(&bars.done));
     }
 
     if (warp < 4) {
