@@ -17,15 +17,17 @@
 //                             with the row, so the one-row-per-lane reads below are conflict free).  Nothing
 //                             waits on a scoreboard: completion lands on an mbarrier
 //                             (cp.async.mbarrier.arrive.noinc), so the bytes in flight are bounded by the ring
-//                             (2 x 32 KB per CTA, 2 CTAs per SM), not by registers.
+//                             (2 x 32 KB per CTA, 2 CTAs per SM), not by registers.  Threads 0-63 also stage the
+//                             mask rows of the tile's (<= 8) children.
 //   warps 0-7  (expanders)  : thread t <-> offspring t of the tile <-> TMEM lane t; the two groups of 4 warps take
-//                             alternate steps.  4 x ld.shared.v4 + the two mask quads (prefetched one step ahead
-//                             with ld.global.nc), one LOP3 per word selects the alleles (h0 & ~M | h1 & M), the
-//                             offspring words go to an output stage in shared memory, then 4 words per plane ->
+//                             alternate steps.  4 x ld.shared.v4 + the two mask quads (broadcast ld.shared; with
+//                             few envs per-lane ld.global.nc, prefetched a step ahead), one LOP3 per word selects
+//                             the alleles (h0 & ~M | h1 & M), the offspring words replace parent A's IN PLACE in
+//                             the stage (the loader warps store them from there), then 4 words per plane ->
 //                             128 prescaled dosage bytes -> tcgen05.st into the A stage in tensor memory.
-//                             The same warps drain the output stages to HBM, four lanes per 64-byte row segment
-//                             (a single storer warp was the bottleneck: 47 us).
-//   warp 8     (digits)     : 1-D bulk copies (TMA) of the digit tiles.
+//                             Before a ring slot is gathered into again, the same warps drain the offspring
+//                             words the expanders left in it to HBM, four lanes per 64-byte row segment.
+//   warp 8     (digits)     : 1-D bulk copies (TMA) of the digit tiles, 4 steps per copy, two halves in flight.
 //   warp 9     (MMA)        : tcgen05.mma.kind::i8, A from TMEM, B from shared memory, D in TMEM.
 //   warps 0-3  (epilogue)   : digits -> int64 -> K-split atomics -> float32 (tc_common.cuh).
 #include <cuda.h>
@@ -39,41 +41,58 @@ using namespace bgtc;
 namespace {
 
 #ifndef XG_R_VAL
-#define XG_R_VAL 2
+#define XG_R_VAL 3
 #endif
 #ifndef XG_S_VAL
-#define XG_S_VAL 4
-#endif
-#ifndef XG_OR_VAL
-#define XG_OR_VAL 2
+#define XG_S_VAL 6
 #endif
 #ifndef XG_CTAS_VAL
 #define XG_CTAS_VAL 2
 #endif
 #ifndef XG_L2HINT_VAL
-#define XG_L2HINT_VAL 0     // L2 prefetch size hint of the cp.async gathers (0 / 128 / 256 bytes)
+#define XG_L2HINT_VAL 0     // L2 prefetch size hint of the cp.async gathers (0 / 128 / 256 bytes): no effect measured at C2
 #endif
-#ifndef XG_PREFETCH_VAL
-#define XG_PREFETCH_VAL 0   // 1: bulk L2 prefetch of this CTA's whole K range of every parent row in the prologue
+#ifndef XG_DEBUG_SKIP
+#define XG_DEBUG_SKIP 0     // timing experiments only (results are wrong): 2 no offspring stores, 4 no gathers
 #endif
-constexpr int XG_R = XG_R_VAL;        // input ring (stages of 4 steps)
-constexpr int XG_S = XG_S_VAL;        // A (TMEM) / B (smem) stages (steps); a separate, deeper digit ring with its own
-                                      // tcgen05.commit per step measured slower (51.2 vs 47.0 us at C2)
-constexpr int XG_OR = XG_OR_VAL;      // output ring (stages of 4 steps)
+constexpr int XG_R = XG_R_VAL;        // stage ring (stages of 4 steps), used IN PLACE: gathered parents -> offspring
+constexpr int XG_S = XG_S_VAL;        // A stages in tensor memory (steps); handed over in PAIRS of steps
+constexpr int XG_SP = XG_S / 2;       // pair stages: one barrier round and one tcgen05.commit per two steps (the MMA warp's
+                                      // fixed costs -- mbarrier wait, commit -- were the pipeline's bottleneck per step)
+constexpr int XG_BP_MAX = 8;          // digit ring: up to 8 pairs of steps ahead
 constexpr int XG_CTAS = XG_CTAS_VAL;  // CTAs per SM
 constexpr int XG_SPS = 4;             // steps per stage: 64 B per row and plane
+constexpr int XG_MC = 8;              // children per tile whose mask rows are staged in shared memory
 constexpr int XG_LOADER_WARP0 = 10, XG_LOADERS = 128;
 constexpr int XG_THREADS = (XG_LOADER_WARP0 + 4) * 32;
-constexpr uint32_t XG_ROW = 16 * XG_SPS;           // bytes per row and plane in a stage
-constexpr uint32_t XG_CHUNK = TILE_M * XG_ROW;     // one plane of a stage: 128 rows x 64 B
-constexpr uint32_t XG_IN_BYTES = 4 * XG_CHUNK;     // parent A planes 0/1, parent B planes 0/1
-constexpr uint32_t XG_OUT_BYTES = 2 * XG_CHUNK;    // offspring planes 0/1
+constexpr uint32_t XG_ROW = 16 * XG_SPS;                // bytes per row and plane in a stage
+constexpr uint32_t XG_CHUNK = TILE_M * XG_ROW;          // one plane of a stage: 128 rows x 64 B
+constexpr uint32_t XG_IN_BYTES = 4 * XG_CHUNK;          // parent A planes 0/1 (-> offspring planes 0/1), parent B planes 0/1
+constexpr uint32_t XG_MASK_BYTES = XG_MC * 2 * XG_ROW;  // mask rows of up to 8 children
 constexpr uint32_t XG_NOROW = 0xFFFFFFFFu;
 
+#ifndef XG_TRACE
+#define XG_TRACE 0   // 1: CTA (XG_TRACE_CTA, 0) records clock64() stamps of its pipeline events (diagnostics build only)
+#endif
+#if XG_TRACE
+#ifndef XG_TRACE_CTA
+#define XG_TRACE_CTA 0
+#endif
+__device__ long long xg_trace_buf[16 * 64];
+#define XG_STAMP(slot, idx)                                                                                              \
+    do {                                                                                                                 \
+        if (blockIdx.x == XG_TRACE_CTA && blockIdx.y == 0 && (idx) < 64) xg_trace_buf[(slot) * 64 + (idx)] = clock64(); \
+    } while (0)
+#else
+#define XG_STAMP(slot, idx) \
+    do {                    \
+    } while (0)
+#endif
+
 struct XGBars {
-    uint64_t raw_full[XG_R], raw_empty[XG_R];
-    uint64_t out_full[XG_OR], out_empty[XG_OR];
-    uint64_t a_full[XG_S], a_empty[XG_S], b_full[XG_S];
+    uint64_t raw_full[XG_R], stage_done[XG_R];
+    uint64_t a_full[XG_SP], a_empty[XG_SP];
+    uint64_t b_full[XG_BP_MAX], b_empty[XG_BP_MAX];
     uint64_t done;
 };
 
@@ -111,10 +130,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 // that 8 consecutive rows reading the same quarter hit 8 different 16-byte bank groups
 __device__ __forceinline__ uint32_t swz(int t, int q) { return (uint32_t)t * XG_ROW + (uint32_t)((q ^ ((t >> 1) & 3)) * 16); }
 
-// smem: input ring [XG_R][4][128][64 B], output ring [XG_OR][2][128][64 B], B stages [XG_S][N/8][8 ki][8][16 B]
+// smem: stage ring [XG_R][4][128][64 B], mask ring [XG_R][8 children][2][64 B], digit ring [nbp pairs][2 steps][N/8][8 ki][8][16 B]
 __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
-    cross_gebv_kernel(const XGArgs fa, const int8_t *__restrict__ bdig, int N, int T, int steps_total, int steps_per_split,
-                      unsigned long long *__restrict__ acc, unsigned int *__restrict__ tile_cnt,
+    cross_gebv_kernel(const XGArgs fa, const int8_t *__restrict__ bdig, int N, int T, int nbp, int steps_total,
+                      int steps_per_split, unsigned long long *__restrict__ acc, unsigned int *__restrict__ tile_cnt,
                       const double *__restrict__ inv_scale, float *__restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -126,14 +145,20 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
     __shared__ uint32_t row_src[2 * TILE_M], row_msk[2 * TILE_M], row_out[TILE_M];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) XG_STAMP(15, 0);
     const uint32_t in_base = smem_u32(smem);
-    const uint32_t out_base = in_base + XG_R * XG_IN_BYTES;
-    const uint32_t b_base0 = out_base + XG_OR * XG_OUT_BYTES;
+    const uint32_t mask_base = in_base + XG_R * XG_IN_BYTES;
+    const uint32_t b_base0 = mask_base + XG_R * XG_MASK_BYTES;
     const uint32_t b_bytes = (uint32_t)N * STEP_K;
     const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
     const int s_begin = blockIdx.y * steps_per_split;                              // a multiple of XG_SPS (launcher)
     const int nst = min(steps_total, s_begin + steps_per_split) - s_begin;          // a multiple of XG_SPS too
     const int nstages = nst / XG_SPS;
+    // child-major tile rows: R <-> (child R / E, env R % E); the tile spans children i0 .. i0 + nchild - 1
+    const int64_t last_row = min(fa.rows, row0 + TILE_M) - 1;
+    const int64_t i0 = row0 / fa.E;
+    const int nchild = (int)(last_row / fa.E - i0) + 1;
+    const bool mask_smem = nchild <= XG_MC;  // else (few envs): every thread fetches its own mask words from L2
 
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
@@ -149,16 +174,15 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
     if (tid == 0) {
         for (int i = 0; i < XG_R; ++i) {
             mbar_init(smem_u32(&bars.raw_full[i]), XG_LOADERS);  // one cp.async completion arrival per loader thread
-            mbar_init(smem_u32(&bars.raw_empty[i]), 8);          // the 8 expander warps
+            mbar_init(smem_u32(&bars.stage_done[i]), 8);         // the 8 expander warps: offspring words are in place
         }
-        for (int i = 0; i < XG_OR; ++i) {
-            mbar_init(smem_u32(&bars.out_full[i]), 8);   // the 8 expander warps
-            mbar_init(smem_u32(&bars.out_empty[i]), 4);  // the 4 loader / storer warps
-        }
-        for (int i = 0; i < XG_S; ++i) {
-            mbar_init(smem_u32(&bars.a_full[i]), 4);   // the 4 warps of the group that filled the stage
+        for (int i = 0; i < XG_SP; ++i) {
+            mbar_init(smem_u32(&bars.a_full[i]), 8);   // the 8 expander warps: both steps of the pair are in tensor memory
             mbar_init(smem_u32(&bars.a_empty[i]), 1);  // tcgen05.commit
+        }
+        for (int i = 0; i < XG_BP_MAX; ++i) {
             mbar_init(smem_u32(&bars.b_full[i]), 1);   // expect_tx arrival of the digit loader
+            mbar_init(smem_u32(&bars.b_empty[i]), 1);  // tcgen05.commit
         }
         mbar_init(smem_u32(&bars.done), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -168,13 +192,14 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
         const int64_t R = row0 + t;
         uint32_t src = XG_NOROW, msk = 0, orow = XG_NOROW;
         if (R < fa.rows) {
-            const int64_t i = R / fa.E, e = R % fa.E;  // child-major tile rows
+            const int64_t i = R / fa.E, e = R - i * fa.E;
             orow = (uint32_t)(e * fa.n + i);
             int64_t a = fa.parents[(int64_t)orow * 2 + p];
             a += a < 0 ? fa.n_src : 0;  // jnp indexing: negatives wrap once, then clamp
             a = a < 0 ? 0 : (a > fa.n_src - 1 ? fa.n_src - 1 : a);
             src = (uint32_t)(((e * fa.n_src + a) * 2) * fa.W4);
-            msk = (uint32_t)((2 * i + p) * fa.W4);
+            // mask row 2i + p: its offset in the global mask array, or (smem mode) its byte offset in a mask stage
+            msk = mask_smem ? (uint32_t)((2 * (i - i0) + p) * XG_ROW) : (uint32_t)((2 * i + p) * fa.W4);
         }
         row_src[k] = src;
         row_msk[k] = msk;
@@ -189,80 +214,128 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
     if (warp < 8) {
         // ---------------- expanders: group g takes the steps j with j % 2 == g ----------------
         const int g = warp >> 2, r = tid & (TILE_M - 1);
+        const bool stamp = (warp & 3) == 0 && lane == 0;
         const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quadrant
-        const uint4 *mrow_a = fa.mask + row_msk[2 * r] + s_begin, *mrow_b = fa.mask + row_msk[2 * r + 1] + s_begin;
-        uint4 ma_next = __ldg(mrow_a + g), mb_next = __ldg(mrow_b + g);
+        const uint32_t msk_a = row_msk[2 * r], msk_b = row_msk[2 * r + 1];
+        const uint4 *mrow_a = fa.mask + (mask_smem ? 0u : msk_a) + s_begin, *mrow_b = fa.mask + (mask_smem ? 0u : msk_b) + s_begin;
+        uint4 ma_next = make_uint4(0, 0, 0, 0), mb_next = ma_next;
+        if (!mask_smem) {
+            ma_next = __ldg(mrow_a + g);
+            mb_next = __ldg(mrow_b + g);
+        }
+        int ap = 0;  // pair stage of step j = (j / 2) % XG_SP; group g fills half g of it
+        uint32_t a_use = 0;
         for (int st = 0; st < nstages; ++st) {
-            const int rs = st % XG_R, os = st % XG_OR;
+            const int rs = st % XG_R;
             mbar_wait(smem_u32(&bars.raw_full[rs]), (st / XG_R) & 1);
-            if (st >= XG_OR) mbar_wait(smem_u32(&bars.out_empty[os]), ((st / XG_OR) - 1) & 1);
-            const uint32_t in_stage = in_base + rs * XG_IN_BYTES, out_stage = out_base + os * XG_OUT_BYTES;
+            if (stamp) XG_STAMP(2 + g, st);  // raw_full seen
+            const uint32_t stage = in_base + rs * XG_IN_BYTES, mstage = mask_base + rs * XG_MASK_BYTES;
 #pragma unroll
             for (int k = 0; k < XG_SPS / 2; ++k) {
                 const int q = 2 * k + g, j = XG_SPS * st + q;  // quarter of the stage row, step of this CTA
                 const uint32_t off = swz(r, q);
-                const uint4 a0 = lds128(in_stage + off), a1 = lds128(in_stage + XG_CHUNK + off);
-                const uint4 b0 = lds128(in_stage + 2 * XG_CHUNK + off), b1 = lds128(in_stage + 3 * XG_CHUNK + off);
-                if (k == XG_SPS / 2 - 1) {  // last read of this input stage: hand it back to the loaders
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[rs]));
-                }
-                const uint4 ma = ma_next, mb = mb_next;
-                if (j + 2 < nst) {  // masks of this thread's next step
-                    ma_next = __ldg(mrow_a + j + 2);
-                    mb_next = __ldg(mrow_b + j + 2);
+                const uint4 a0 = lds128(stage + off), a1 = lds128(stage + XG_CHUNK + off);
+                const uint4 b0 = lds128(stage + 2 * XG_CHUNK + off), b1 = lds128(stage + 3 * XG_CHUNK + off);
+                uint4 ma, mb;
+                if (mask_smem) {  // all lanes of a warp share a child when E % 32 == 0: broadcast reads
+                    ma = lds128(mstage + msk_a + q * 16);
+                    mb = lds128(mstage + msk_b + q * 16);
+                } else {
+                    ma = ma_next;
+                    mb = mb_next;
+                    if (j + 2 < nst) {  // masks of this thread's next step
+                        ma_next = __ldg(mrow_a + j + 2);
+                        mb_next = __ldg(mrow_b + j + 2);
+                    }
                 }
                 const uint4 x0 = blend4(a0, a1, ma), x1 = blend4(b0, b1, mb);
-                sts128(out_stage + off, x0);
-                sts128(out_stage + XG_CHUNK + off, x1);
+                // offspring words replace parent A's in the stage (same thread, same slots): the loader warps store them
+                sts128(stage + off, x0);
+                sts128(stage + XG_CHUNK + off, x1);
+                if (k == XG_SPS / 2 - 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars.stage_done[rs]));
+                }
                 // dosage bytes -> tensor memory
                 const DosageFields f = dosage_fields(x0, x1);
-                const int as = j % XG_S;
-                if (j >= XG_S) mbar_wait(smem_u32(&bars.a_empty[as]), ((j / XG_S) - 1) & 1);  // MMAs of the previous use retired
+                if (stamp) XG_STAMP(6, j);  // fields done, about to wait a_empty
+                if (a_use > 0) mbar_wait(smem_u32(&bars.a_empty[ap]), (a_use - 1) & 1);  // MMAs of the previous use retired
+                if (stamp) XG_STAMP(7, j);  // a_empty seen
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                dosage_to_tmem(tmem_a + lane_sel + (uint32_t)as * (STEP_K / 4), f);
+                dosage_to_tmem(tmem_a + lane_sel + (uint32_t)(2 * ap + g) * (STEP_K / 4), f);
+                if (stamp) XG_STAMP(8, j);  // TMEM stores complete
+                if (lane == 0 && g == 0) XG_STAMP(warp == 0 ? 0 : (warp == 1 ? 1 : (warp == 2 ? 4 : 9)), j >> 1);  // per warp of group 0
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[as]));
+                if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[ap]));
+                if (++ap == XG_SP) {
+                    ap = 0;
+                    ++a_use;
+                }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars.out_full[os]));
         }
     } else if (warp == 8) {
         if (lane == 0) {
-            // ---------------- digit tiles (1-D bulk copies) ----------------
-            for (int j = 0; j < nst; ++j) {
-                const int bs = j % XG_S;
-                if (j >= XG_S) mbar_wait(smem_u32(&bars.a_empty[bs]), ((j / XG_S) - 1) & 1);
-                const uint32_t full = smem_u32(&bars.b_full[bs]);
-                mbar_arrive_expect_tx(full, b_bytes);
+            // ---------------- digit tiles: one bulk copy (TMA) per pair of steps, up to nbp pairs ahead ----------------
+            const uint32_t pair_bytes = 2 * b_bytes;
+            // the whole digit range of this CTA -> L2 now (the table is usually cold: a step streams more than L2 holds),
+            // so that the ring below is fed at L2 latency
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(bdig + (int64_t)s_begin * b_bytes), "r"((uint32_t)nst * b_bytes)
+                         : "memory");
+            int slot = 0;
+            uint32_t use = 0;
+            for (int pj = 0; pj < nst / 2; ++pj) {
+                if (use > 0) mbar_wait(smem_u32(&bars.b_empty[slot]), (use - 1) & 1);
+                const uint32_t full = smem_u32(&bars.b_full[slot]);
+                mbar_arrive_expect_tx(full, pair_bytes);
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 b_base0 + bs * b_bytes),
-                             "l"(bdig + (int64_t)(s_begin + j) * b_bytes), "r"(b_bytes), "r"(full)
+                                 b_base0 + slot * pair_bytes),
+                             "l"(bdig + ((int64_t)s_begin + 2 * pj) * b_bytes), "r"(pair_bytes), "r"(full)
                              : "memory");
+                if (++slot == nbp) {
+                    slot = 0;
+                    ++use;
+                }
             }
         }
     } else if (warp == 9) {
-        // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues ----------------
+        // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues; one round per PAIR of steps ----------------
         const uint32_t idesc = idesc_u8s8(N);
-        for (int j = 0; j < nst; ++j) {
-            const int as = j % XG_S;
-            const uint32_t par = (j / XG_S) & 1;
-            const uint32_t a_taddr = tmem_a + (uint32_t)as * (STEP_K / 4);
-            const uint64_t bdesc = make_smem_desc(b_base0 + as * b_bytes, 128, 1024);
-            mbar_wait(smem_u32(&bars.b_full[as]), par);
-            mbar_wait(smem_u32(&bars.a_full[as]), par);
+        int ap = 0, slot = 0;
+        uint32_t a_par = 0, b_par = 0;
+        for (int pj = 0; pj < nst / 2; ++pj) {
+            const uint32_t a_taddr = tmem_a + (uint32_t)(2 * ap) * (STEP_K / 4);
+            const uint64_t bdesc = make_smem_desc(b_base0 + (uint32_t)slot * 2 * b_bytes, 128, 1024);
+            mbar_wait(smem_u32(&bars.b_full[slot]), b_par);
+            if (lane == 0) XG_STAMP(10, pj);  // digit pair landed
+            mbar_wait(smem_u32(&bars.a_full[ap]), a_par);
+            if (lane == 0) XG_STAMP(11, pj);  // A pair full
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             __syncwarp();
 #pragma unroll
-            for (int kk = 0; kk < STEP_K / 32; ++kk)  // +16 in the descriptor's address field = +256 bytes
-                mma_i8_ts_warp(tmem_d, a_taddr + 8 * kk, bdesc + 16 * kk, idesc, (j > 0 || kk > 0) ? 1u : 0u);
-            mma_commit_warp(smem_u32(&bars.a_empty[as]));
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int kk = 0; kk < STEP_K / 32; ++kk)  // +16 in the descriptor's address field = +256 bytes
+                    mma_i8_ts_warp(tmem_d, a_taddr + h * (STEP_K / 4) + 8 * kk, bdesc + (uint64_t)(h * (b_bytes >> 4)) + 16 * kk, idesc,
+                                   (pj > 0 || h > 0 || kk > 0) ? 1u : 0u);
+            if (lane == 0) XG_STAMP(5, pj);  // 8 MMAs issued
+            mma_commit_warp(smem_u32(&bars.a_empty[ap]));
+            mma_commit_warp(smem_u32(&bars.b_empty[slot]));
+            if (lane == 0) XG_STAMP(12, pj);  // commits issued
+            if (++ap == XG_SP) {
+                ap = 0;
+                a_par ^= 1;
+            }
+            if (++slot == nbp) {
+                slot = 0;
+                b_par ^= 1;
+            }
         }
         mma_commit_warp(smem_u32(&bars.done));
     } else {
         // ---------------- loaders / storers: thread u covers quarter q = u & 3 of rows (u >> 2) + 32k ----------------
-        // per iteration: gather stage `it` (both planes of both parents, 16 cp.async in flight, no register staging),
-        // then drain the offspring stage the expanders finished XG_R stages earlier (coalesced 128-bit stores)
+        // per iteration: drain the offspring words of the stage that used this ring slot XG_R stages ago (coalesced
+        // 128-bit stores), then gather the next stage into it (both planes of both parents: 16 cp.async in flight per
+        // thread, no register staging) plus, threads u < 64, one 16-byte piece of the tile's mask rows
         const int u = tid - XG_LOADER_WARP0 * 32, q = u & 3;
         uint32_t src[4][2], dst[4], orow[4];
         uint32_t valid = 0;
@@ -276,43 +349,18 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
             else src[k][0] = src[k][1] = 0;
             dst[k] = swz(t, q);
         }
-#if XG_PREFETCH_VAL
-        if (q == 0) {
-            // whole K range of this CTA, one request per row and plane (measured slower at C2: 51.6 vs 47.0 us)
-            const uint32_t pbytes = (uint32_t)nst * 16;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((valid >> k) & 1) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint4 *a = fa.pop + src[k][c >> 1] + (c & 1) * fa.W4 + s_begin;
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(pbytes) : "memory");
-                    }
-                }
-        }
-#endif
+        // mask piece of this thread: row (2 * (i0 + u / 8) + (u / 4) % 2), quarter q
+        const int mrow = u >> 2;  // 0 .. 15 for u < 64
+        const bool mask_loader = mask_smem && u < 2 * XG_MC * 4;
+        const bool mask_valid = mask_loader && (mrow >> 1) < nchild;
+        const uint4 *msrc = fa.mask + (mask_valid ? (2 * i0 + mrow) * fa.W4 : 0);
         for (int it = 0; it < nstages + XG_R; ++it) {
-            if (it < nstages) {
-                const int rs = it % XG_R;
-                if (it >= XG_R) mbar_wait(smem_u32(&bars.raw_empty[rs]), ((it / XG_R) - 1) & 1);
-                const int w4 = s_begin + XG_SPS * it + q;
-                const uint32_t stage = in_base + rs * XG_IN_BYTES;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t nbytes = ((valid >> k) & 1) ? 16u : 0u;  // 0: zero-fill, nothing is read
-                    const uint32_t d = stage + dst[k];
-                    cp_async16(d, fa.pop + src[k][0] + w4, nbytes);
-                    cp_async16(d + XG_CHUNK, fa.pop + src[k][0] + fa.W4 + w4, nbytes);
-                    cp_async16(d + 2 * XG_CHUNK, fa.pop + src[k][1] + w4, nbytes);
-                    cp_async16(d + 3 * XG_CHUNK, fa.pop + src[k][1] + fa.W4 + w4, nbytes);
-                }
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars.raw_full[rs])) : "memory");
-            }
-            const int so = it - XG_R;
-            if (so >= 0) {
-                const int os = so % XG_OR;
-                mbar_wait(smem_u32(&bars.out_full[os]), (so / XG_OR) & 1);
-                const uint32_t stage = out_base + os * XG_OUT_BYTES;
+            const int rs = it % XG_R;
+            const uint32_t stage = in_base + rs * XG_IN_BYTES;
+            if (it >= XG_R) {
+                const int so = it - XG_R;
+                mbar_wait(smem_u32(&bars.stage_done[rs]), (so / XG_R) & 1);
+                if (u == 0) XG_STAMP(14, so);  // stage_done seen
                 const int w4 = s_begin + XG_SPS * so + q;
                 uint4 v[4][2];
 #pragma unroll
@@ -320,25 +368,43 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
                     v[k][0] = lds128(stage + dst[k]);
                     v[k][1] = lds128(stage + XG_CHUNK + dst[k]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars.out_empty[os]));  // the stage is in registers
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (orow[k] != XG_NOROW) {
+                    if (orow[k] != XG_NOROW && !(XG_DEBUG_SKIP & 2)) {
                         uint4 *o = fa.out_pop + (int64_t)orow[k] * 2 * fa.W4 + w4;
                         o[0] = v[k][0];
                         o[fa.W4] = v[k][1];
                     }
             }
+            if (it < nstages) {
+                // (the slots gathered into below were read by THIS thread's stores above, or by the expanders that
+                //  signalled stage_done: no other thread still needs them)
+                if (u == 0) XG_STAMP(13, it);  // gathers of stage `it` issued
+                const int w4 = s_begin + XG_SPS * it + q;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t nbytes = (((valid >> k) & 1) && !(XG_DEBUG_SKIP & 4)) ? 16u : 0u;  // 0: zero-fill, nothing is read
+                    const uint32_t d = stage + dst[k];
+                    cp_async16(d, fa.pop + src[k][0] + w4, nbytes);
+                    cp_async16(d + XG_CHUNK, fa.pop + src[k][0] + fa.W4 + w4, nbytes);
+                    cp_async16(d + 2 * XG_CHUNK, fa.pop + src[k][1] + w4, nbytes);
+                    cp_async16(d + 3 * XG_CHUNK, fa.pop + src[k][1] + fa.W4 + w4, nbytes);
+                }
+                if (mask_loader) cp_async16(mask_base + rs * XG_MASK_BYTES + (uint32_t)mrow * XG_ROW + q * 16, msrc + w4, mask_valid ? 16u : 0u);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars.raw_full[rs])) : "memory");
+            }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
 
+    if (tid == 0) XG_STAMP(15, 1);
     if (warp < 4) {
         mbar_wait(smem_u32(&bars.done), 0);
+        if (tid == 0) XG_STAMP(15, 2);
         digits_epilogue(tmem_d, tid, warp, row0, fa.rows, T, acc, tile_cnt, inv_scale, out, &last_cta_flag, blockIdx.x, gridDim.y,
                         row_out);
     }
+    if (tid == 0) XG_STAMP(15, 3);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 9)
@@ -346,6 +412,13 @@ __global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
 }
 
 }  // namespace
+
+#if XG_TRACE
+extern "C" int bg_debug_read_trace(long long *host, int n)
+{
+    return (int)cudaMemcpyFromSymbol(host, xg_trace_buf, sizeof(long long) * n);
+}
+#endif
 
 int bg_tc_reserve_scratch(bg_engine *eng, int scratch, int64_t total, int64_t tiles, cudaStream_t st);
 void bg_tc_split(int64_t tiles, int steps, int64_t target, int multiple, int *ksplit_out, int *sps_out);
@@ -355,7 +428,7 @@ bool bg_cross_gebv_fused_ok(const bg_engine *eng, int64_t E, int64_t n_src, int6
 {
     if (!eng || !eng->d_wdig || eng->mut_thr) return false;
     const int N = eng->tc_N;
-    const size_t smem = (size_t)XG_R * XG_IN_BYTES + (size_t)XG_OR * XG_OUT_BYTES + (size_t)XG_S * N * STEP_K;
+    const size_t smem = (size_t)XG_R * (XG_IN_BYTES + XG_MASK_BYTES) + (size_t)2 * 2 * N * STEP_K;
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
     if (smem > (size_t)eng->max_smem_optin || d_cols + XG_S * (STEP_K / 4) > 512) return false;
@@ -368,6 +441,7 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
                                int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st)
 {
     BG_REQUIRE(eng && eng->d_wdig, BG_ESTATE, "engine has no tensor-core digit table");
+    static_assert(XG_S % 2 == 0, "the two expander groups alternate over an even number of A stages");
     const int T = eng->T, N = eng->tc_N;
     const int steps = (int)eng->tc_steps;  // a multiple of 8: rows are padded to 32 words
     const int64_t rows = E * n;
@@ -377,14 +451,21 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
     BG_REQUIRE((int64_t)eng->Wpad / 4 * 2 * (n_src > n ? n_src : n) * E < (int64_t(1) << 32), BG_ELIMIT,
                "population too large for the fused kernel's 32-bit row offsets");
 
-    const size_t smem = (size_t)XG_R * XG_IN_BYTES + (size_t)XG_OR * XG_OUT_BYTES + (size_t)XG_S * N * STEP_K;
+    // digit ring: nbp pairs of steps, as deep as fits beside the stage ring with XG_CTAS CTAs per SM
+    const size_t rings = (size_t)XG_R * (XG_IN_BYTES + XG_MASK_BYTES), b_bytes = (size_t)N * STEP_K;
+    const size_t per_cta = 228 * 1024 / XG_CTAS - 1024 - 3584;  // minus the reserved KB and the static arrays
+    int nbp = per_cta > rings ? (int)((per_cta - rings) / (2 * b_bytes)) : 0;
+    if (nbp > XG_BP_MAX) nbp = XG_BP_MAX;
+    if (nbp < 2) nbp = 2;
+    const size_t smem = rings + (size_t)nbp * 2 * b_bytes;
     BG_REQUIRE(smem <= (size_t)eng->max_smem_optin, BG_ELIMIT, "too many traits for the fused cross+GEBV tile");
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
     uint32_t tcols = 32;
     while (tcols < d_cols + XG_S * (STEP_K / 4)) tcols <<= 1;
+    BG_REQUIRE(tcols <= 512, BG_ELIMIT, "too many traits for the fused kernel's tensor memory");
     int resident = (int)(512 / tcols);
-    const int by_smem = (int)(227 * 1024 / (smem + 1024));
+    const int by_smem = (int)(228 * 1024 / (smem + 1024 + 3584));
     if (by_smem < resident) resident = by_smem;
     if (resident > XG_CTAS) resident = XG_CTAS;
     if (resident < 1) resident = 1;
@@ -407,8 +488,8 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
     fa.rows = rows;
     fa.W4 = eng->Wpad / 4;
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
-    cross_gebv_kernel<<<grid, XG_THREADS, smem, st>>>(fa, eng->d_wdig, N, T, steps, sps, eng->d_acc2[0], eng->d_tile_cnt[0],
-                                                      eng->d_inv_scale, gebv_out);
+    cross_gebv_kernel<<<grid, XG_THREADS, smem, st>>>(fa, eng->d_wdig, N, T, nbp, steps, sps, eng->d_acc2[0],
+                                                      eng->d_tile_cnt[0], eng->d_inv_scale, gebv_out);
     BG_LAUNCHED();
     return BG_OK;
 }
