@@ -340,6 +340,9 @@ int bg_gather_individuals(bg_engine *eng, const uint32_t *src, const int32_t *id
 // ---- crossover-mask slots (vector env) ------------------------------------------------------
 static bool slot_matches(const bg_mask_slot &sl, const uint32_t key[2], int layout, int schedule, int64_t rows)
 {
+    // timing experiments only (results are wrong): any generated slot serves any key -> no mask kernel in the step
+    static const bool reuse = getenv("BG_DEBUG_REUSE_MASKS") != nullptr;
+    if (reuse && sl.valid && sl.rows == rows) return true;
     return sl.valid && sl.key[0] == key[0] && sl.key[1] == key[1] && sl.layout == layout && sl.schedule == schedule &&
            sl.rows == rows;
 }

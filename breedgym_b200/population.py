@@ -36,6 +36,15 @@ class PackedPopulation:
         self.words = words
         self._bool = None
 
+    @classmethod
+    def _trusted(cls, sim, words: torch.Tensor) -> "PackedPopulation":
+        """Wrap words the library has just produced (skips the layout checks: the env's per-step path)."""
+        self = cls.__new__(cls)
+        self.sim = sim
+        self.words = words
+        self._bool = None
+        return self
+
     # ---- array-like surface --------------------------------------------------
     @property
     def shape(self) -> Tuple[int, ...]:

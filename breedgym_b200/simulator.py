@@ -100,6 +100,7 @@ class Simulator:
         self._key_state = np.zeros(2, dtype=np.uint32)   # random_key, advanced in place by the C key chain
         self._chain_out = np.zeros(4, dtype=np.uint32)   # [k, next k]
         self._key_ptr, self._chain_ptr = _lib.nptr(self._key_state), _lib.nptr(self._chain_out)
+        self._chain_out_addr = self._chain_out.ctypes.data
         self._chain_fn = _lib.load().bg_key_chain_next
         self.mutation = float(mutation)
         self.device = _resolve_device(device)

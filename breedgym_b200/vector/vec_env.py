@@ -151,15 +151,22 @@ class VecBreedGym(VectorEnv):
             if a.ndim != 3 or a.shape[0] != E or a.shape[2] != 2:
                 raise ValueError(f"actions must have shape ({E}, n, 2), got {a.shape}")
             n = a.shape[1]
-            io = self._host_io(a.shape, T)
+            io = self._io
+            if io is None or io["shape"] != a.shape:
+                io = self._host_io(a.shape, T)
             io["act_np"][...] = a  # int64 -> int32 conversion happens in this copy
-            out = sim._empty_words(E, n)
-            sim._next_key(lookahead=True)  # advances the chain; k and the next k sit in sim._chain_out
-            kp = sim._chain_out.ctypes.data
-            _lib.check(self._vec_step_fn(
+            out = torch.empty((E, n, 2, sim.words_per_row), dtype=torch.int32, device=self.device)
+            # random_key, k = split(random_key): advances the chain; k and the next k sit in sim._chain_out
+            rc = sim._chain_fn(sim._key_ptr, sim._layout_id, sim._chain_ptr)
+            if rc:
+                _lib.check(rc)
+            kp = sim._chain_out_addr
+            rc = self._vec_step_fn(
                 sim._engine, src.data_ptr(), out.data_ptr(), io["act_pin"], io["act_dev"], E, n_src, n, kp, kp + 8,
                 sim._layout_id, sim._schedule_id, io["gebv_dev"], io["rew_dev"] if need_reward else None,
-                io["gebv_pin"], io["rew_pin"] if need_reward else None, sim._stream()))
+                io["gebv_pin"], io["rew_pin"] if need_reward else None, sim._stream())
+            if rc:
+                _lib.check(rc)
             infos = {"GEBV": io["gebv_np"].copy()}
             rews = io["rew_np"].copy() if need_reward else np.zeros(E)
         else:
@@ -206,7 +213,7 @@ class VecBreedGym(VectorEnv):
                 infos = {"GEBV": gebv_dev}
                 rews = rew_dev if need_reward else self._zero_rewards()
 
-        self.populations = PackedPopulation(sim, out)
+        self.populations = PackedPopulation._trusted(sim, out)
         self.step_idx += 1
         if done and self.autoreset:
             self.reset()
