@@ -40,15 +40,23 @@ struct RowParams {
 // `one` is the constant 1 read from the kernel parameters: x0 = x1 * one + x0 keeps the Threefry
 // additions on the FMA pipe (IMAD) while rotate (SHF) and xor (LOP3) use the ALU pipe, so the two
 // integer pipes share the ~100 operations of a block instead of all of them queueing on one.
+#ifndef BG_TF_MULROT
+#define BG_TF_MULROT 0x00000   // bit i: round i rotates through a 64-bit multiply (FMA pipe) instead of a funnel shift (ALU pipe)
+#endif
 template <int N>
 __device__ __forceinline__ void tf2x32_n(const TfKey &k, uint32_t (&x0)[N], uint32_t (&x1)[N], const uint32_t one)
 {
-#define BG_R(r)                                  \
-    _Pragma("unroll") for (int u = 0; u < N; ++u) \
-    {                                            \
-        x0[u] = x1[u] * one + x0[u];             \
-        x1[u] = __funnelshift_l(x1[u], x1[u], r); \
-        x1[u] ^= x0[u];                          \
+    // x * 2^r as a 64-bit product (IMAD.WIDE): lo | hi is the rotation, and the OR folds into the round's XOR (one LOP3)
+#define BG_R(i, r)                                                                     \
+    _Pragma("unroll") for (int u = 0; u < N; ++u)                                      \
+    {                                                                                  \
+        x0[u] = x1[u] * one + x0[u];                                                   \
+        if ((BG_TF_MULROT >> (i)) & 1) {                                               \
+            const unsigned long long p = (unsigned long long)x1[u] * (unsigned long long)(one << (r)); \
+            x1[u] = ((uint32_t)p | (uint32_t)(p >> 32)) ^ x0[u];                       \
+        } else {                                                                       \
+            x1[u] = __funnelshift_l(x1[u], x1[u], r) ^ x0[u];                          \
+        }                                                                              \
     }
 #define BG_INJ(a, b, c)                          \
     _Pragma("unroll") for (int u = 0; u < N; ++u) \
@@ -57,11 +65,11 @@ __device__ __forceinline__ void tf2x32_n(const TfKey &k, uint32_t (&x0)[N], uint
         x1[u] += (b) + (c);                      \
     }
     BG_INJ(k.k0, k.k1, 0u)
-    BG_R(13) BG_R(15) BG_R(26) BG_R(6) BG_INJ(k.k1, k.k2, 1u)
-    BG_R(17) BG_R(29) BG_R(16) BG_R(24) BG_INJ(k.k2, k.k0, 2u)
-    BG_R(13) BG_R(15) BG_R(26) BG_R(6) BG_INJ(k.k0, k.k1, 3u)
-    BG_R(17) BG_R(29) BG_R(16) BG_R(24) BG_INJ(k.k1, k.k2, 4u)
-    BG_R(13) BG_R(15) BG_R(26) BG_R(6) BG_INJ(k.k2, k.k0, 5u)
+    BG_R(0, 13) BG_R(1, 15) BG_R(2, 26) BG_R(3, 6) BG_INJ(k.k1, k.k2, 1u)
+    BG_R(4, 17) BG_R(5, 29) BG_R(6, 16) BG_R(7, 24) BG_INJ(k.k2, k.k0, 2u)
+    BG_R(8, 13) BG_R(9, 15) BG_R(10, 26) BG_R(11, 6) BG_INJ(k.k0, k.k1, 3u)
+    BG_R(12, 17) BG_R(13, 29) BG_R(14, 16) BG_R(15, 24) BG_INJ(k.k1, k.k2, 4u)
+    BG_R(16, 13) BG_R(17, 15) BG_R(18, 26) BG_R(19, 6) BG_INJ(k.k2, k.k0, 5u)
 #undef BG_R
 #undef BG_INJ
 }
@@ -94,7 +102,8 @@ __device__ __forceinline__ void draw_bits(uint32_t *S, const TfKey key, const ui
                 const uint32_t g = g0 + u;
                 const uint32_t bA = __ballot_sync(FULL, (x0[u] >> 9) < tA[u]);
                 const uint32_t bB = __ballot_sync(FULL, (x1[u] >> 9) < tB[u]);
-                if (g < G) {
+                // recombination events are rare (r ~ 1e-3): one warp-uniform test skips the stitching for most groups
+                if ((bA | bB) != 0u && g < G) {
                     if (lane == 0 && bA) atomicOr(&S[g], bA);
                     if (lane == 1 && bB) atomicOr(&S[wsB + g], bB << sh);
                     if (lane == 2 && sh && (bB >> (32 - sh))) atomicOr(&S[wsB + g + 1], bB >> (32 - sh));
