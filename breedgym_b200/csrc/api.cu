@@ -89,19 +89,22 @@ int bg_key_split(const uint32_t key[2], int64_t num, int layout, uint32_t *out)
     return BG_OK;
 }
 
-int bg_key_chain_next(uint32_t state[2], int layout, uint32_t out[4])
+int bg_key_chain_next(uint32_t state[2], int layout, uint32_t out[6])
 {
     BG_REQUIRE(state && out, BG_EINVAL, "bg_key_chain_next: bad argument");
     BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
     const TfKey cur = tf_make_key(state[0], state[1]);
     const TfKey after = tf_split_at(cur, 0, 2, layout), k = tf_split_at(cur, 1, 2, layout);
-    const TfKey next_k = tf_split_at(after, 1, 2, layout);
+    const TfKey after2 = tf_split_at(after, 0, 2, layout), next_k = tf_split_at(after, 1, 2, layout);
+    const TfKey next2_k = tf_split_at(after2, 1, 2, layout);
     state[0] = after.k0;
     state[1] = after.k1;
     out[0] = k.k0;
     out[1] = k.k1;
     out[2] = next_k.k0;
     out[3] = next_k.k1;
+    out[4] = next2_k.k0;
+    out[5] = next2_k.k1;
     return BG_OK;
 }
 
@@ -384,13 +387,13 @@ static int slot_generate(bg_engine *eng, bg_mask_slot &sl, const uint32_t key[2]
 // masks for `key`, usable by work enqueued on `st` after this returns
 static int masks_acquire(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, cudaStream_t st, int *slot)
 {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < BG_MASK_SLOTS; ++i)
         if (slot_matches(eng->slots[i], key, layout, schedule, rows)) {
             BG_CUDA(cudaStreamWaitEvent(st, eng->slots[i].ready, 0));  // generated ahead of time (or earlier on st)
             *slot = i;
             return BG_OK;
         }
-    const int i = eng->last_slot ^ 1;
+    const int i = (eng->last_slot + 1) % BG_MASK_SLOTS;
     bg_mask_slot &sl = eng->slots[i];
     if (sl.ready_set) BG_CUDA(cudaStreamWaitEvent(st, sl.ready, 0));  // a stale lookahead may still be writing the slot
     if (sl.freed_set) BG_CUDA(cudaStreamWaitEvent(st, sl.freed, 0));
@@ -409,19 +412,28 @@ static int masks_release(bg_engine *eng, int slot, cudaStream_t st)
     return BG_OK;
 }
 
-// start generating the masks of the NEXT cross key on the side stream (other slot than `cur`)
+// start generating the masks of an UPCOMING cross key on the side stream, in a slot that holds neither the current
+// masks (`cur`) nor those of another upcoming key (`keep`, -1: none); returns the slot used (or already holding them)
 // `after_step`: start only once the kernels of the current step are done (their `freed` record).  The host-facing
 // step synchronises and leaves the GPU idle while the host works: the integer-bound mask kernel then runs in that gap
-// instead of competing with the step kernel for issue slots.  The device-resident pipeline has no gap: there the two
-// overlap.
-static int masks_lookahead(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, int cur, bool after_step)
+// instead of competing with the step kernel for issue slots.  The device-resident pipeline has no gap: there the mask
+// kernels run TWO steps ahead, so that they only fill the slots the step kernels leave free and never delay their start.
+static int masks_lookahead(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, int cur, int keep,
+                           bool after_step, int *used)
 {
-    for (int i = 0; i < 2; ++i)
-        if (slot_matches(eng->slots[i], key, layout, schedule, rows)) return BG_OK;
+    for (int i = 0; i < BG_MASK_SLOTS; ++i)
+        if (slot_matches(eng->slots[i], key, layout, schedule, rows)) {
+            *used = i;
+            return BG_OK;
+        }
     if (!eng->side) BG_CUDA(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
-    bg_mask_slot &sl = eng->slots[cur ^ 1];
+    int v = -1;
+    for (int i = 0; i < BG_MASK_SLOTS; ++i)
+        if (i != cur && i != keep) v = i;
+    bg_mask_slot &sl = eng->slots[v];
     if (after_step && eng->slots[cur].freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, eng->slots[cur].freed, 0));
-    if (sl.freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, sl.freed, 0));  // its last reader (an earlier blend) is done
+    if (sl.freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, sl.freed, 0));  // its last reader (an earlier step) is done
+    *used = v;
     return slot_generate(eng, sl, key, layout, schedule, rows, eng->side);
 }
 
@@ -473,7 +485,14 @@ static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *p
     rc = masks_release(eng, slot, st);
     if (rc) return rc;
     static const bool no_lookahead = getenv("BG_NO_LOOKAHEAD") != nullptr;  // diagnostics
-    if (next_key && !no_lookahead) rc = masks_lookahead(eng, next_key, layout, schedule, 2 * n, slot, lookahead_after_step);
+    if (next_key && !no_lookahead) {
+        // next_key[0..1]: the next step's key, next_key[2..3]: the one after it
+        int s1 = -1, s2 = -1;
+        rc = masks_lookahead(eng, next_key, layout, schedule, 2 * n, slot, -1, lookahead_after_step, &s1);
+        static const bool one_ahead = getenv("BG_LOOKAHEAD1") != nullptr;  // diagnostics
+        if (!rc && !lookahead_after_step && !one_ahead)
+            rc = masks_lookahead(eng, next_key + 2, layout, schedule, 2 * n, slot, s1, false, &s2);
+    }
     return rc;
 }
 

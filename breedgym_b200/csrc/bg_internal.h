@@ -22,6 +22,8 @@ struct bg_mask_slot {
     bool ready_set = false, freed_set = false;
 };
 
+constexpr int BG_MASK_SLOTS = 3;  // current step + two steps of lookahead
+
 struct bg_engine {
     int device = 0;
     int sm_count = 148;
@@ -39,8 +41,8 @@ struct bg_engine {
     int64_t tc_steps = 0;             // 128-marker K steps (= Wpad / 4)
     int32_t tc_N = 0;                 // 8*T rounded up to a multiple of 16 (0: tensor-core path unavailable)
     // grow-only scratch
-    bg_mask_slot slots[2];
-    int last_slot = 1;
+    bg_mask_slot slots[BG_MASK_SLOTS];
+    int last_slot = BG_MASK_SLOTS - 1;
     cudaStream_t side = nullptr;        // lookahead stream
     uint32_t *d_mut = nullptr;          // mutation scratch of bg_meiosis_masks
     size_t mut_cap = 0;                 // words

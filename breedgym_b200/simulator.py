@@ -98,7 +98,7 @@ class Simulator:
         self._layout_id = _lib.LAYOUT_ID[rng_layout]
         self._schedule_id = _lib.SCHEDULE_ID[key_schedule]
         self._key_state = np.zeros(2, dtype=np.uint32)   # random_key, advanced in place by the C key chain
-        self._chain_out = np.zeros(4, dtype=np.uint32)   # [k, next k]
+        self._chain_out = np.zeros(6, dtype=np.uint32)   # [k, next k, the k after that]
         self._key_ptr, self._chain_ptr = _lib.nptr(self._key_state), _lib.nptr(self._chain_out)
         self._chain_out_addr = self._chain_out.ctypes.data
         self._chain_fn = _lib.load().bg_key_chain_next
@@ -182,7 +182,7 @@ class Simulator:
         the NEXT call will get (valid unless `set_seed` intervenes).  One C call, no allocation; the
         returned arrays are views of a scratch buffer that the next call overwrites."""
         _lib.check(self._chain_fn(self._key_ptr, self._layout_id, self._chain_ptr))
-        return (self._chain_out[:2], self._chain_out[2:]) if lookahead else self._chain_out[:2].copy()
+        return (self._chain_out[:2], self._chain_out[2:4]) if lookahead else self._chain_out[:2].copy()
 
     def _layout(self) -> int:
         return _lib.LAYOUT_ID[self.rng_layout]

@@ -68,8 +68,8 @@ int bg_random_bits(const uint32_t key[2], int64_t n, int layout, uint32_t *out /
  * out[r][e][:] = random_bits(sub, n).  keys: [E][2], out: [rounds][E][n] */
 int bg_shuffle_sort_keys(const uint32_t *keys, int64_t E, int64_t n, int layout, int rounds, uint32_t *out);
 /* one link of chromax's chain `random_key, k = split(random_key)`: state <- split(state)[0],
- * out[0..1] = k, out[2..3] = the k the NEXT call will return (lookahead for bg_vec_step) */
-int bg_key_chain_next(uint32_t state[2], int layout, uint32_t out[4]);
+ * out[0..1] = k, out[2..3] / out[4..5] = the k the NEXT two calls will return (lookahead for bg_vec_step) */
+int bg_key_chain_next(uint32_t state[2], int layout, uint32_t out[6]);
 /* integer form of `uniform(key) < r`: (bits >> 9) < T,  T = clamp(ceil(r * 2^23), 0, 2^23) */
 int bg_thresholds(const float *r, int64_t m, uint32_t *out /* [m] */);
 
@@ -177,10 +177,11 @@ int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, cons
  * buffers at the boundary: copies actions_host (int32 [E][n][2], pinned or
  * pageable) to `actions_dev`, runs cross -> GEBV (-> max reward), copies
  * gebv/reward back to the host buffers when non-NULL, and synchronises the stream
- * iff any device->host copy was requested.  next_cross_key (may be NULL) is the key
- * the FOLLOWING step will pass as cross_key if nobody reseeds in between: its masks
- * are generated on an internal side stream while this step blends and scores
- * (masks depend on the key chain only); a wrong guess costs nothing but that work. */
+ * iff any device->host copy was requested.  next_cross_key (may be NULL) points to
+ * uint32[4]: the keys the FOLLOWING two steps will pass as cross_key if nobody reseeds
+ * in between (bg_key_chain_next out[2..5]): their masks are generated on an internal
+ * side stream while this step runs (masks depend on the key chain only); a wrong guess
+ * costs nothing but that work. */
 int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_t *actions_host, int32_t *actions_dev,
                 int64_t E, int64_t n_src, int64_t n, const uint32_t cross_key[2], const uint32_t *next_cross_key,
                 int layout, int schedule,

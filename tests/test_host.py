@@ -54,11 +54,13 @@ def test_host_key_chain_matches_oracle(golden):
         for q in (0, 3, 64):
             assert np.array_equal(_lib.key_split_at(_lib.key_data(5), q, 65, layout), jp.split(jp.key(5), 65, layout)[q])
         st = _lib.key_data(21).copy()
-        out = np.zeros(4, dtype=np.uint32)
+        out = np.zeros(6, dtype=np.uint32)
         _lib.check(_lib.load().bg_key_chain_next(_lib.nptr(st), _lib.LAYOUT_ID[layout], _lib.nptr(out)))
         ks = jp.split(jp.key(21), 2, layout)
         assert np.array_equal(st, ks[0]) and np.array_equal(out[:2], ks[1])
-        assert np.array_equal(out[2:], jp.split(ks[0], 2, layout)[1])
+        ks2 = jp.split(ks[0], 2, layout)
+        assert np.array_equal(out[2:4], ks2[1])                          # the key of the next call
+        assert np.array_equal(out[4:], jp.split(ks2[0], 2, layout)[1])   # and of the one after it
     assert _lib.key_data((3 << 32) + 4).tolist() == [3, 4]
     out = (ctypes.c_uint32 * 2)()
     _lib.load().bg_threefry2x32(0x13198A2E, 0x03707344, 0x243F6A88, 0x85A308D3, out)
