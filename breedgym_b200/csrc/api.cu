@@ -365,13 +365,13 @@ static int slot_prepare(bg_engine *eng, bg_mask_slot &sl, int64_t rows)
 }
 
 static int slot_generate(bg_engine *eng, bg_mask_slot &sl, const uint32_t key[2], int layout, int schedule, int64_t rows,
-                         cudaStream_t on)
+                         cudaStream_t on, int small_ctas = 0)
 {
     sl.valid = false;
     int rc = slot_prepare(eng, sl, rows);
     if (rc) return rc;
     rc = bg_launch_meiosis_rows(eng, BG_ROWS_MASK, rows, key, layout, schedule, sl.mask, eng->mut_thr ? sl.mut : nullptr, nullptr,
-                                nullptr, 0, 0, nullptr, on);
+                                nullptr, 0, 0, nullptr, on, small_ctas);
     if (rc) return rc;
     BG_CUDA(cudaEventRecord(sl.ready, on));
     sl.ready_set = true;
@@ -434,7 +434,9 @@ static int masks_lookahead(bg_engine *eng, const uint32_t key[2], int layout, in
     if (after_step && eng->slots[cur].freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, eng->slots[cur].freed, 0));
     if (sl.freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, sl.freed, 0));  // its last reader (an earlier step) is done
     *used = v;
-    return slot_generate(eng, sl, key, layout, schedule, rows, eng->side);
+    // overlapping the step kernel: small CTAs that fit beside its two CTAs per SM
+    static const bool big = getenv("BG_MASK_BIG_CTAS") != nullptr;  // diagnostics
+    return slot_generate(eng, sl, key, layout, schedule, rows, eng->side, (after_step || big) ? 0 : 1);
 }
 
 // gebv_out != nullptr: also score the offspring; fused into one kernel when the tensor-core path applies

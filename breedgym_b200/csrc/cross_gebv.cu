@@ -65,6 +65,9 @@ constexpr int XG_SPS = 4;             // steps per stage: 64 B per row and plane
 constexpr int XG_MC = 8;              // children per tile whose mask rows are staged in shared memory
 constexpr int XG_LOADER_WARP0 = 10, XG_LOADERS = 128;
 constexpr int XG_THREADS = (XG_LOADER_WARP0 + 4) * 32;
+#ifndef XG_REGCAP_THREADS
+#define XG_REGCAP_THREADS 512
+#endif
 constexpr uint32_t XG_ROW = 16 * XG_SPS;                // bytes per row and plane in a stage
 constexpr uint32_t XG_CHUNK = TILE_M * XG_ROW;          // one plane of a stage: 128 rows x 64 B
 constexpr uint32_t XG_IN_BYTES = 4 * XG_CHUNK;          // parent A planes 0/1 (-> offspring planes 0/1), parent B planes 0/1
@@ -131,7 +134,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 __device__ __forceinline__ uint32_t swz(int t, int q) { return (uint32_t)t * XG_ROW + (uint32_t)((q ^ ((t >> 1) & 3)) * 16); }
 
 // smem: stage ring [XG_R][4][128][64 B], mask ring [XG_R][8 children][2][64 B], digit ring [nbp pairs][2 steps][N/8][8 ki][8][16 B]
-__global__ void __launch_bounds__(XG_THREADS, XG_CTAS)
+// launch bounds of 512 threads (448 are launched): caps the kernel at 64 registers per thread, so that two CTAs leave
+// 8192 registers of the SM free -- exactly one 128-thread CTA of the mask kernel, which then runs in the issue slots
+// this (latency-bound) kernel leaves idle instead of displacing its CTAs
+__global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
     cross_gebv_kernel(const XGArgs fa, const int8_t *__restrict__ bdig, int N, int T, int nbp, int steps_total,
                       int steps_per_split, unsigned long long *__restrict__ acc, unsigned int *__restrict__ tile_cnt,
                       const double *__restrict__ inv_scale, float *__restrict__ out)

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) blend_envs_kernel(const uint4 *__restrict
 
 int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_t cross_key[2], int layout, int schedule,
                            uint32_t *mask_out, uint32_t *mut_out, const uint32_t *pop, const int32_t *parents,
-                           int64_t n_src, int64_t dh_offspring, uint32_t *out, cudaStream_t st)
+                           int64_t n_src, int64_t dh_offspring, uint32_t *out, cudaStream_t st, int small_ctas)
 {
     BG_REQUIRE(eng && eng->d_thr, BG_ESTATE, "engine has no map (call bg_engine_set_map)");
     BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
@@ -347,9 +347,12 @@ int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_
     P.dh_offspring = dh_offspring > 0 ? dh_offspring : 1;
     P.out = out;
     P.one = 1u;
-    const int NT = eng->W <= 1024 ? 256 : 1024;
+    // small_ctas: 128-thread CTAs (8192 registers) for mask kernels that run beside the fused step kernel, see cross_gebv.cu
+    int small_nt = 128;
+    if (const char *e = getenv("BG_MASK_NT")) small_nt = atoi(e) >= 32 && atoi(e) <= 256 ? atoi(e) / 32 * 32 : small_nt;  // tuning
+    const int NT = eng->W <= 1024 ? (small_ctas ? small_nt : 256) : 1024;
     void (*kern)(RowParams);
-    if (NT == 256)
+    if (NT <= 256)
         kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 256> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 256>;
     else
         kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 1024> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 1024>;
