@@ -20,6 +20,7 @@ is the reward all-gather on episode ends.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -300,6 +301,11 @@ def run_ours(args):
 
     def timed(fn, steps):
         """K steps bracketed by barrier + synchronize; device time between two CUDA events."""
+        # a full (generation 2) Python garbage collection walks every object the imported packages hold: 40-500 ms,
+        # once every few thousand steps, wherever it happens to fall (seen as one block 5-10x slower than the others).
+        # Collect now and park the survivors in the permanent generation so that none falls inside the timed region.
+        gc.collect()
+        gc.freeze()
         stream = torch.cuda.current_stream(dev)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -405,7 +411,19 @@ def run_ours(args):
     spin_up()
     for i in range(max(W, REPLICAS)):
         host_step(i)
-    t_e2e = max_over_ranks(timed(host_step, K))
+    # timed in blocks (same total K): a block far slower than the others points at the box (clock state, a descheduled
+    # host thread), not at the path; reported beside the total
+    nblk = 4 if K >= 400 else 1
+    blocks = []
+    sampler_e2e = ClockSampler(local_rank)
+    sampler_e2e.start()
+    base = 0
+    for b in range(nblk):
+        kb = K // nblk + (1 if b < K % nblk else 0)
+        blocks.append(timed(lambda i, base=base: host_step(base + i), kb) / kb)
+        base += kb
+    clocks_e2e = sampler_e2e.stop()
+    t_e2e = max_over_ranks(sum(bt * (K // nblk + (1 if b < K % nblk else 0)) for b, bt in enumerate(blocks)))
     h2d = count * N_IND * 2 * 4
     d2h = count * N_IND * 4 + (count * 4) / NUM_GENERATIONS
 
@@ -427,7 +445,8 @@ def run_ours(args):
             "offspring_markers_per_sec": value * N_IND * N_MARKERS,
             "clocks": clocks,
             "e2e": {"value": total_envs * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "VecBreedGym.step(numpy actions) -> numpy GEBV / rewards, one sync per step"},
+                    "api": "VecBreedGym.step(numpy actions) -> numpy GEBV / rewards, one sync per step",
+                    "us_per_step_by_block": [round(1e6 * bt, 1) for bt in blocks], "clocks": clocks_e2e},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "kernels": kernels,

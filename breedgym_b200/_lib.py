@@ -52,7 +52,7 @@ _SIGNATURES = {
     "bg_reduce_mean": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "bg_reset_indices": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "bg_vec_reset": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
-                             c_void_p, c_void_p, c_void_p]),
+                             c_void_p, c_void_p, c_void_p, c_void_p]),
     "bg_vec_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

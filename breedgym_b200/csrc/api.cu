@@ -600,7 +600,7 @@ int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_tot
 
 int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, const uint32_t random_key[2], int64_t E_total,
                  int64_t env_begin, int64_t E, int64_t n, int layout, int32_t *idx_dev, uint32_t *pop_out, float *gebv_dev,
-                 float *gebv_host, void *stream)
+                 float *gebv_host, const float *germ_gebv, void *stream)
 {
     BG_ENTER(eng);
     BG_REQUIRE(germplasm && random_key && idx_dev && pop_out && E > 0 && n > 0 && n_germ > 0, BG_EINVAL, "bg_vec_reset: bad argument");
@@ -609,9 +609,13 @@ int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, cons
     cudaStream_t st = (cudaStream_t)stream;
     int rc = bg_launch_reset_indices(eng, random_key, E_total, env_begin, E, n_germ, n, layout, idx_dev, st);
     if (rc) return rc;
-    rc = bg_launch_gather(germplasm, idx_dev, pop_out, E, n_germ, n, 0, eng->Wpad, st);
+    // a GEBV is a function of the individual alone: with the germplasm's GEBVs at hand the reset infos are gathered
+    // along with the individuals (bit-identical: every GEBV kernel sums the same integers) instead of recomputed
+    const bool gather_gebv = gebv_dev && germ_gebv;
+    rc = bg_launch_gather(germplasm, idx_dev, pop_out, E, n_germ, n, 0, eng->Wpad, st, gather_gebv ? germ_gebv : nullptr,
+                          gather_gebv ? gebv_dev : nullptr, eng->T);
     if (rc) return rc;
-    if (gebv_dev) {
+    if (gebv_dev && !gather_gebv) {
         rc = bg_launch_gebv(eng, pop_out, E * n, gebv_dev, 0, st);
         if (rc) return rc;
     }

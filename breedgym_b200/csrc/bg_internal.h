@@ -109,6 +109,7 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
 int bg_launch_pack(const uint8_t *in, uint32_t *out, int64_t rows, int64_t m, int W, int Wpad, cudaStream_t st);
 int bg_launch_unpack(const uint32_t *in, uint8_t *out, int64_t rows, int64_t m, int Wpad, cudaStream_t st);
 int bg_launch_gather(const uint32_t *src, const int32_t *idx, uint32_t *dst, int64_t E, int64_t n_src, int64_t n,
-                     int64_t src_env_rows, int Wpad, cudaStream_t st);
+                     int64_t src_env_rows, int Wpad, cudaStream_t st, const float *src_vals = nullptr, float *dst_vals = nullptr,
+                     int T = 0);
 int bg_launch_reset_indices(bg_engine *eng, const uint32_t key[2], int64_t E_total, int64_t env_begin, int64_t E, int64_t N,
                             int64_t n, int layout, int32_t *idx_out, cudaStream_t st);

@@ -60,9 +60,11 @@ __device__ __forceinline__ int64_t norm_index(int64_t a, int64_t n)
 }
 
 // dst[e][r] = src[e*src_env_rows + idx[e][r]] ; one CTA per destination individual
+// src_vals (optional): per-individual values [rows of src][T] (e.g. GEBVs) gathered along with the individuals
 __global__ void __launch_bounds__(128) gather_kernel(const uint4 *__restrict__ src, const int32_t *__restrict__ idx,
                                                      uint4 *__restrict__ dst, int64_t n_src, int64_t n,
-                                                     int64_t src_env_rows, int V)
+                                                     int64_t src_env_rows, int V, const float *__restrict__ src_vals,
+                                                     float *__restrict__ dst_vals, int T)
 {
     const int64_t d = blockIdx.x;  // e*n + r
     const int64_t e = d / n;
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(128) gather_kernel(const uint4 *__restrict__ s
     const uint4 *sp = src + s * V;
     uint4 *dp = dst + d * V;
     for (int v = threadIdx.x; v < V; v += blockDim.x) dp[v] = __ldg(sp + v);
+    if (src_vals)
+        for (int t = threadIdx.x; t < T; t += blockDim.x) dst_vals[d * T + t] = __ldg(src_vals + s * T + t);
 }
 
 // One CTA per env.  smem: sort keys [N], permutation x [N], scratch y [N].
@@ -134,11 +138,12 @@ int bg_launch_unpack(const uint32_t *in, uint8_t *out, int64_t rows, int64_t m, 
 }
 
 int bg_launch_gather(const uint32_t *src, const int32_t *idx, uint32_t *dst, int64_t E, int64_t n_src, int64_t n,
-                     int64_t src_env_rows, int Wpad, cudaStream_t st)
+                     int64_t src_env_rows, int Wpad, cudaStream_t st, const float *src_vals, float *dst_vals, int T)
 {
     if (E * n == 0) return BG_OK;
     BG_REQUIRE(E * n < (int64_t(1) << 31), BG_ELIMIT, "gather grid too large");
-    gather_kernel<<<(unsigned)(E * n), 128, 0, st>>>((const uint4 *)src, idx, (uint4 *)dst, n_src, n, src_env_rows, 2 * Wpad / 4);
+    gather_kernel<<<(unsigned)(E * n), 128, 0, st>>>((const uint4 *)src, idx, (uint4 *)dst, n_src, n, src_env_rows, 2 * Wpad / 4,
+                                                     src_vals, dst_vals, T);
     BG_LAUNCHED();
     return BG_OK;
 }

@@ -20,6 +20,7 @@ single-GPU env -- no data-path collective, only the reward all-gather
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 from typing import Optional, Tuple, Union
 
@@ -81,6 +82,7 @@ class VecBreedGym(VectorEnv):
         self._io = None
         self._h2d_done = None
         self._vec_step_fn = _lib.load().bg_vec_step
+        self._germ_gebv = None
 
     def _set_spaces(self):
         n, m = self.individual_per_gen, self.germplasm.shape[1]
@@ -239,6 +241,8 @@ class VecBreedGym(VectorEnv):
         idx = torch.empty((E, n), dtype=torch.int32, device=self.device)
         words = sim._empty_words(E, n)
         germ = self.germplasm.words.contiguous()
+        if self._germ_gebv is None and not os.environ.get("BG_NO_GERM_GEBV"):  # once: the reset infos are gathered from the germplasm's GEBVs
+            self._germ_gebv = sim._gebv(self.germplasm).to(torch.float32).contiguous()  # raw kernel output, as bg_vec_reset computes
         host_info = self.info_device == "host"
         if host_info:
             io = self._host_io((E, n, 2), T)
@@ -250,7 +254,7 @@ class VecBreedGym(VectorEnv):
         # the draw, the gather from the germplasm and the reset infos
         _lib.check(_lib.load().bg_vec_reset(sim._engine, germ.data_ptr(), germ.shape[0], _lib.nptr(key), total, begin, E, n,
                                             sim._layout_id, idx.data_ptr(), words.data_ptr(), gebv_dev_ptr, gebv_host_ptr,
-                                            sim._stream()))
+                                            self._germ_gebv.data_ptr() if self._germ_gebv is not None else None, sim._stream()))
         self.random_key = _lib.key_split_at(self.random_key, 0, total + 1, sim.rng_layout)
         self._reset_indices = idx
         self.populations = PackedPopulation(sim, words)

@@ -167,10 +167,12 @@ int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_tot
 /* VecBreedGym.reset in one call (breedgym/vector/vec_env.py:109-130): bg_reset_indices, the gather
  * of the drawn individuals from the germplasm (packed [n_germ][2][Wpad]) into pop_out
  * ([E][n][2][Wpad]) and, when gebv_dev is non-NULL, the reset infos GEBV_model(populations)
- * ([E][n][T]); gebv_host non-NULL copies them to the host and synchronises the stream. */
+ * ([E][n][T]); gebv_host non-NULL copies them to the host and synchronises the stream.
+ * germ_gebv (device float32 [n_germ][T] = bg_gebv of the germplasm, or NULL): when given, the
+ * reset infos are gathered from it along with the individuals instead of recomputed. */
 int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, const uint32_t random_key[2], int64_t E_total,
                  int64_t env_begin, int64_t E, int64_t n, int layout, int32_t *idx_dev, uint32_t *pop_out, float *gebv_dev,
-                 float *gebv_host, void *stream);
+                 float *gebv_host, const float *germ_gebv, void *stream);
 
 /* ---- one-call vector-env step ------------------------------------------------
  * VecBreedGym.step hot path (breedgym/vector/vec_env.py:88-100) with host
