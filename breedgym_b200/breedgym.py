@@ -72,7 +72,10 @@ class BreedGym(Env):
         self.action_space = spaces.Sequence(spaces.Tuple((spaces.Discrete(n), spaces.Discrete(n))))
 
     def _update_spaces(self):
-        self._set_spaces(self.population.shape)
+        shape = self.population.shape
+        if getattr(self, "_spaces_shape", None) != shape:  # the spaces depend on the population size only
+            self._set_spaces(shape)
+            self._spaces_shape = shape
 
     # ---- gym API -----------------------------------------------------------------
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):

@@ -304,7 +304,10 @@ class Simulator:
 
     def GEBV(self, population) -> pd.DataFrame:
         gebv = self.GEBV_model(population)
-        return pd.DataFrame(gebv.cpu().numpy(), columns=self.trait_names)
+        cols = getattr(self, "_trait_index", None)
+        if cols is None or list(cols) != list(self.trait_names):  # building the column Index is most of DataFrame()'s cost
+            cols = self._trait_index = pd.Index(self.trait_names)
+        return pd.DataFrame(gebv.cpu().numpy(), columns=cols, copy=False)
 
     @property
     def max_gebv(self):
