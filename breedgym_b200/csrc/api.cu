@@ -212,7 +212,6 @@ int bg_engine_destroy(bg_engine *eng)
         cudaFree(eng->d_acc);
         for (int i = 0; i < 2; ++i) {
             cudaFree(eng->d_acc2[i]);
-            cudaFree(eng->d_tile_cnt[i]);
         }
         if (eng->side2) {
             cudaStreamSynchronize(eng->side2);

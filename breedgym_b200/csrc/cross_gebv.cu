@@ -139,13 +139,12 @@ __device__ __forceinline__ uint32_t swz(int t, int q) { return (uint32_t)t * XG_
 // this (latency-bound) kernel leaves idle instead of displacing its CTAs
 __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
     cross_gebv_kernel(const XGArgs fa, const int8_t *__restrict__ bdig, int N, int T, int nbp, int steps_total,
-                      int steps_per_split, unsigned long long *__restrict__ acc, unsigned int *__restrict__ tile_cnt,
+                      int steps_per_split, unsigned long long *__restrict__ acc,
                       const double *__restrict__ inv_scale, float *__restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) XGBars bars;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ uint32_t last_cta_flag;
     // per offspring t of the tile: uint4 offsets of its parents' rows (plane 0; plane 1 follows) and mask rows, and
     // its row index in out_pop / gebv (XG_NOROW past the end)
     __shared__ uint32_t row_src[2 * TILE_M], row_msk[2 * TILE_M], row_out[TILE_M];
@@ -407,8 +406,7 @@ __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
     if (warp < 4) {
         mbar_wait(smem_u32(&bars.done), 0);
         if (tid == 0) XG_STAMP(15, 2);
-        digits_epilogue(tmem_d, tid, warp, row0, fa.rows, T, acc, tile_cnt, inv_scale, out, &last_cta_flag, blockIdx.x, gridDim.y,
-                        row_out);
+        digits_epilogue(tmem_d, tid, warp, row0, fa.rows, T, acc, inv_scale, out, gridDim.y, row_out);
     }
     if (tid == 0) XG_STAMP(15, 3);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -495,7 +493,7 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
     fa.W4 = eng->Wpad / 4;
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
     cross_gebv_kernel<<<grid, XG_THREADS, smem, st>>>(fa, eng->d_wdig, N, T, nbp, steps, sps, eng->d_acc2[0],
-                                                      eng->d_tile_cnt[0], eng->d_inv_scale, gebv_out);
+                                                      eng->d_inv_scale, gebv_out);
     BG_LAUNCHED();
     return BG_OK;
 }

@@ -55,13 +55,12 @@ struct T2Bars {
 // smem: raw ring [T2_R][256 plane-rows][16 B], then B stages [T2_S][N/8][8 ki][8][16 B]
 __global__ void __launch_bounds__(T2_THREADS, 4)
     gebv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, int64_t rows, const int8_t *__restrict__ bdig, int N, int T,
-                    int steps_total, int steps_per_split, unsigned long long *__restrict__ acc, unsigned int *__restrict__ tile_cnt,
+                    int steps_total, int steps_per_split, unsigned long long *__restrict__ acc,
                     const double *__restrict__ inv_scale, float *__restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) T2Bars bars;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ uint32_t last_cta_flag;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw_base = smem_u32(smem);
@@ -177,7 +176,7 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
 
     if (warp < 4) {
         mbar_wait(smem_u32(&bars.done), 0);
-        digits_epilogue(tmem_d, tid, warp, row0, rows, T, acc, tile_cnt, inv_scale, out, &last_cta_flag, blockIdx.x, gridDim.y);
+        digits_epilogue(tmem_d, tid, warp, row0, rows, T, acc, inv_scale, out, gridDim.y);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -187,7 +186,7 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
 
 }  // namespace
 
-// zero-invariant scratch of the K-split kernels: accumulators [rows][T] and one arrival counter per tile
+// zero-invariant scratch of the K-split kernels: accumulators [rows][T] (sum in the low 56 bits, arrival count on top)
 int bg_tc_reserve_scratch(bg_engine *eng, int scratch, int64_t total, int64_t tiles, cudaStream_t st)
 {
     if (eng->acc2_cap[scratch] < (size_t)total) {
@@ -197,14 +196,6 @@ int bg_tc_reserve_scratch(bg_engine *eng, int scratch, int64_t total, int64_t ti
         BG_CUDA(cudaMalloc(&eng->d_acc2[scratch], (size_t)total * sizeof(unsigned long long)));
         BG_CUDA(cudaMemsetAsync(eng->d_acc2[scratch], 0, (size_t)total * sizeof(unsigned long long), st));
         eng->acc2_cap[scratch] = (size_t)total;
-    }
-    if (eng->tile_cap[scratch] < (size_t)tiles) {
-        if (eng->d_tile_cnt[scratch]) BG_CUDA(cudaFree(eng->d_tile_cnt[scratch]));
-        eng->d_tile_cnt[scratch] = nullptr;
-        eng->tile_cap[scratch] = 0;
-        BG_CUDA(cudaMalloc(&eng->d_tile_cnt[scratch], (size_t)tiles * sizeof(unsigned int)));
-        BG_CUDA(cudaMemsetAsync(eng->d_tile_cnt[scratch], 0, (size_t)tiles * sizeof(unsigned int), st));
-        eng->tile_cap[scratch] = (size_t)tiles;
     }
     return BG_OK;
 }
@@ -220,7 +211,7 @@ void bg_tc_split(int64_t tiles, int steps, int64_t target, int multiple, int *ks
     // int32 accumulators: a 128-marker step adds at most 16 * 43520 to a digit sum (prescaled bytes <= 128,
     // |digit| <= 128), so at most 3000 steps per CTA keeps every digit sum below 2^31
     if (ksplit < (steps + 2999) / 3000) ksplit = (steps + 2999) / 3000;
-    if (ksplit > 65535) ksplit = 65535;
+    if (ksplit > KSPLIT_MAX) ksplit = KSPLIT_MAX;  // 8-bit arrival count in the accumulators (tc_common.cuh)
     int sps = (steps + ksplit - 1) / ksplit;
     sps = (sps + multiple - 1) / multiple * multiple;
     *ksplit_out = (steps + sps - 1) / sps;
@@ -286,8 +277,7 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
     const int8_t *bd = eng->d_wdig;
     const double *inv = eng->d_inv_scale;
     unsigned long long *acc = eng->d_acc2[scratch];
-    unsigned int *cnt = eng->d_tile_cnt[scratch];
-    BG_CUDA(cudaLaunchKernelEx(&cfg, gebv_tc2_kernel, tmap, rows, bd, N, T, steps, sps, acc, cnt, inv, out));
+    BG_CUDA(cudaLaunchKernelEx(&cfg, gebv_tc2_kernel, tmap, rows, bd, N, T, steps, sps, acc, inv, out));
     BG_LAUNCHED();
     return BG_OK;
 }

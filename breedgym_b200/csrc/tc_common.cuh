@@ -153,19 +153,22 @@ __device__ __forceinline__ void mma_commit(uint32_t bar)
 }
 
 // Epilogue of warps 0-3 (thread t <-> accumulator row t <-> TMEM lane t): digits -> int64 (exactly 64x the
-// fixed-point sum, shifted back), K-split partials meet in 64-bit integer atomics and the LAST CTA of a tile
-// converts to float32 and re-zeroes the accumulators (they are all zero between launches): no finalize launch.
+// fixed-point sum, shifted back).  K-split partials meet in ONE 64-bit atomic per value: the high 56 bits carry the sum
+// (two's complement, |sum| < 2^55 by construction of the fixed-point scale, api.cu), the low 8 bits count arrivals
+// (<= 255, so they never carry into the sum), so the CTA whose atomicAdd returns nsplit - 1 arrivals holds the
+// complete sum in the returned value, converts it to float32 and puts
+// the zero back (the accumulators are all zero between launches): one L2 round trip, no fence, no barrier, no
+// finalize launch.  (The earlier protocol -- partial atomics, __threadfence, tile counter, last CTA re-reads -- cost
+// three dependent round trips: ~4300 of the ~36000 cycles a CTA of the fused kernel lives.)
+constexpr int KSPLIT_MAX = 255;
 __device__ __forceinline__ void digits_epilogue(uint32_t tmem_d, int tid, int warp, int64_t row0, int64_t rows, int T,
-                                                unsigned long long *__restrict__ acc, unsigned int *__restrict__ tile_cnt,
-                                                const double *__restrict__ inv_scale, float *__restrict__ out,
-                                                uint32_t *last_cta_flag, unsigned tile_idx, unsigned nsplit,
-                                                const uint32_t *out_row_map = nullptr)
+                                                unsigned long long *__restrict__ acc, const double *__restrict__ inv_scale,
+                                                float *__restrict__ out, unsigned nsplit, const uint32_t *out_row_map = nullptr)
 {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int64_t row = row0 + tid;  // accumulator slot; the result goes to row `orow` of `out`
     const int64_t orow = out_row_map ? (int64_t)out_row_map[tid] : row;
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-    const bool single = nsplit == 1;  // no K split: this CTA holds the whole sum
     for (int t = 0; t < T; ++t) {
         uint32_t v[8];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -176,27 +179,19 @@ __device__ __forceinline__ void digits_epilogue(uint32_t tmem_d, int tid, int wa
         unsigned long long sum = 0;  // modular arithmetic: the true total fits in int64
 #pragma unroll
         for (int d = 7; d >= 0; --d) sum = (sum << 8) + (unsigned long long)(long long)(int32_t)v[d];
-        sum = (unsigned long long)((long long)sum >> 6);  // prescaled operand: every (partial) sum is exactly 64x
+        long long total = (long long)sum >> 6;  // prescaled operand: every (partial) sum is exactly 64x
         if (row < rows) {
-            if (single)
-                out[orow * T + t] = (float)((double)(long long)sum * inv_scale[t]);
-            else
-                atomicAdd(acc + row * T + t, sum);  // integer partial sums: order independent
-        }
-    }
-    if (!single) {
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) *last_cta_flag = atomicAdd(tile_cnt + tile_idx, 1u) == nsplit - 1 ? 1u : 0u;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (*last_cta_flag) {
-            __threadfence();
-            if (row < rows)
-                for (int t = 0; t < T; ++t) {
-                    const unsigned long long tot = atomicExch(acc + row * T + t, 0ull);
-                    out[orow * T + t] = (float)((double)(long long)tot * inv_scale[t]);
+            bool complete = nsplit == 1;  // no K split: this CTA holds the whole sum
+            if (!complete) {
+                const unsigned long long mine = ((unsigned long long)total << 8) + 1ull;
+                const unsigned long long old = atomicAdd(acc + row * T + t, mine);
+                if ((unsigned)(old & 0xFFull) == nsplit - 1) {  // the last of the nsplit partial sums
+                    total = (long long)(old + mine) >> 8;  // arithmetic shift: the 56-bit sum, sign-extended
+                    acc[row * T + t] = 0ull;
+                    complete = true;
                 }
-            if (tid == 0) tile_cnt[tile_idx] = 0u;
+            }
+            if (complete) out[orow * T + t] = (float)((double)total * inv_scale[t]);
         }
     }
 }
