@@ -409,3 +409,18 @@ def test_sharded_env_over_nccl_matches_unsharded(cuda_device):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "multi-gpu check ok" in r.stdout
+
+
+def test_reset_infos_gathered_from_germplasm_equal_rescored(cuda_device, monkeypatch):
+    """VecBreedGym.reset gathers the reset infos from the germplasm's GEBVs (a GEBV is a function of the individual
+    alone); re-scoring the drawn populations (BG_NO_GERM_GEBV=1, what vec_env.py:130 does) gives the same bits."""
+    kw = dict(num_envs=5, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=37)
+    env_a = gym().make("VecBreedGym", **kw)
+    pop_a, infos_a = env_a.reset(seed=11)
+    monkeypatch.setenv("BG_NO_GERM_GEBV", "1")
+    env_b = gym().make("VecBreedGym", **kw)
+    pop_b, infos_b = env_b.reset(seed=11)
+    assert env_a._germ_gebv is not None and env_b._germ_gebv is None
+    assert np.array_equal(np.asarray(pop_a), np.asarray(pop_b))
+    assert np.array_equal(infos_a["GEBV"], infos_b["GEBV"])
+    assert np.array_equal(infos_a["GEBV"], env_a.get_info()["GEBV"])
