@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) {
+    if (tid == 8 * 32) {  // a thread without a row-table entry: the table build below is the prologue's critical path
         for (int i = 0; i < XG_R; ++i) {
             mbar_init(smem_u32(&bars.raw_full[i]), XG_LOADERS);  // one cp.async completion arrival per loader thread
             mbar_init(smem_u32(&bars.stage_done[i]), 8);         // the 8 expander warps: offspring words are in place
@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
         const int64_t R = row0 + t;
         uint32_t src = XG_NOROW, msk = 0, orow = XG_NOROW;
         if (R < fa.rows) {
-            const int64_t i = R / fa.E, e = R - i * fa.E;
+            const uint32_t i32 = (uint32_t)R / (uint32_t)fa.E;  // rows < 2^31 (launcher): 32-bit division
+            const int64_t i = i32, e = (uint32_t)R - i32 * (uint32_t)fa.E;
             orow = (uint32_t)(e * fa.n + i);
             int64_t a = fa.parents[(int64_t)orow * 2 + p];
             a += a < 0 ? fa.n_src : 0;  // jnp indexing: negatives wrap once, then clamp
