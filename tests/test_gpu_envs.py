@@ -424,3 +424,26 @@ def test_reset_infos_gathered_from_germplasm_equal_rescored(cuda_device, monkeyp
     assert np.array_equal(np.asarray(pop_a), np.asarray(pop_b))
     assert np.array_equal(infos_a["GEBV"], infos_b["GEBV"])
     assert np.array_equal(infos_a["GEBV"], env_a.get_info()["GEBV"])
+
+
+@pytest.mark.parametrize("k,n_crosses,layout", [(10, None, "legacy"), (10, 20, "legacy"), (7, 3, "partitionable"), (20, 190, "legacy")])
+def test_selection_scores_device_index_math_equals_host(cuda_device, k, n_crosses, layout):
+    """SelectionScores' GPU translation (stable sort, bg_reset_indices permutation, gathers, repeat) == the NumPy one
+    (jaxlike: lax.top_k, random.choice(replace=False), repeat), including tied scores."""
+    from breedgym_b200 import _lib
+    from breedgym_b200.vector import SelectionScores, VecBreedGym
+
+    num_envs, n = 6, 200
+    env = SelectionScores(VecBreedGym(num_envs=num_envs, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n,
+                                      rng_layout=layout), k=k, n_crosses=n_crosses)
+    env.reset(seed=3)
+    rng = np.random.default_rng(k)
+    for trial in range(3):
+        scores = rng.standard_normal((num_envs, n)).astype(np.float32)
+        scores[:, rng.integers(0, n, 40)] = 0.25  # ties: the lower index wins
+        key = np.array(rng.integers(0, 2**32, 2), dtype=np.uint32)
+        keys = _lib.key_split(key, num_envs + 1, layout)
+        host = env._convert_actions(scores, keys[1:])
+        dev = env._convert_actions_device(scores, key).cpu().numpy()
+        assert dev.shape == (num_envs, n, 2) and dev.dtype == np.int32
+        assert np.array_equal(dev, host)
