@@ -213,12 +213,6 @@ int bg_engine_destroy(bg_engine *eng)
         for (int i = 0; i < 2; ++i) {
             cudaFree(eng->d_acc2[i]);
         }
-        if (eng->side2) {
-            cudaStreamSynchronize(eng->side2);
-            cudaStreamDestroy(eng->side2);
-        }
-        if (eng->ev_half) cudaEventDestroy(eng->ev_half);
-        if (eng->ev_half_done) cudaEventDestroy(eng->ev_half_done);
     }
     delete eng;
     return BG_OK;
@@ -452,30 +446,6 @@ static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *p
     const bg_mask_slot &sl = eng->slots[slot];
     if (gebv_out && !no_fuse && bg_cross_gebv_fused_ok(eng, E, n_src, n)) {
         rc = bg_launch_cross_gebv_fused(eng, pop, parents, sl.mask, out, E, n_src, n, gebv_out, st);
-    } else if (gebv_out && eng->tc_N && E >= 16 && getenv("BG_SPLIT") != nullptr) {
-        // Opt-in experiment: two halves of the env batch, software-pipelined over two streams -- the GEBV of the first
-        // half (integer / tensor bound) runs on `side2` while the second half is still blending (memory bound).
-        // Measured at C2: 88 us per step against 77 us unsplit (the half-size kernels lose more than the overlap wins).
-        if (!eng->side2) {
-            BG_CUDA(cudaStreamCreateWithFlags(&eng->side2, cudaStreamNonBlocking));
-            BG_CUDA(cudaEventCreateWithFlags(&eng->ev_half, cudaEventDisableTiming));
-            BG_CUDA(cudaEventCreateWithFlags(&eng->ev_half_done, cudaEventDisableTiming));
-        }
-        const uint32_t *mut = eng->mut_thr ? sl.mut : nullptr;
-        const int64_t Ea = E / 2, Eb = E - Ea;
-        const int64_t pop_env = n_src * 2 * eng->Wpad, out_env = n * 2 * eng->Wpad;
-        rc = bg_launch_blend(eng, pop, parents, sl.mask, mut, out, Ea, n_src, n, st);
-        if (rc) return rc;
-        BG_CUDA(cudaEventRecord(eng->ev_half, st));
-        BG_CUDA(cudaStreamWaitEvent(eng->side2, eng->ev_half, 0));
-        rc = bg_launch_gebv_tc2(eng, out, Ea * n, gebv_out, eng->side2, 1);
-        if (rc) return rc;
-        BG_CUDA(cudaEventRecord(eng->ev_half_done, eng->side2));
-        rc = bg_launch_blend(eng, pop + Ea * pop_env, parents + Ea * 2 * n, sl.mask, mut, out + Ea * out_env, Eb, n_src, n, st);
-        if (rc) return rc;
-        rc = bg_launch_gebv_tc2(eng, out + Ea * out_env, Eb * n, gebv_out + Ea * n * eng->T, st, 0);
-        if (rc) return rc;
-        BG_CUDA(cudaStreamWaitEvent(st, eng->ev_half_done, 0));
     } else {
         // blend and GEBV are adjacent in the stream (no event between them) so that the GEBV kernel's
         // programmatic dependent launch can overlap its prologue with the blend's tail

@@ -51,8 +51,6 @@ struct bg_engine {
     unsigned long long *d_acc2[2] = {nullptr, nullptr};  // gebv_tc2: all-zero between launches (one set per stream)
     size_t acc2_cap[2] = {0, 0};
     size_t tc2_optin[2] = {48 * 1024, 48 * 1024};  // dynamic smem already opted into (plain, fused kernel)
-    cudaStream_t side2 = nullptr;          // second half of a split step scores here while the first half still blends
-    cudaEvent_t ev_half = nullptr, ev_half_done = nullptr;
 };
 
 void bg_set_error(const std::string &msg);

@@ -124,8 +124,18 @@ def _pairs_from_scores(scores, n_crosses: int, device) -> torch.Tensor:
     (truncate, or pad with the last pair)."""
     s = torch.as_tensor(scores, dtype=torch.float32, device=device)
     E, n = s.shape[0], s.shape[-1]
-    vals, idx = torch.sort(s.reshape(E, -1), dim=1, descending=True, stable=True)
-    vals, idx = vals[:, :n_crosses], idx[:, :n_crosses]
+    flat = s.reshape(E, -1) + 0.0  # -0.0 -> +0.0: the two compare equal, so they must get the same key
+    # top-n_crosses with jax.lax.top_k's order (descending, ties -> lower flat index) WITHOUT sorting all n^2 scores:
+    # 64-bit keys = (order-preserving integer image of the float32 score, inverted flat index) are unique, so a plain
+    # (unstable) top-k of the keys is that order exactly
+    bits = flat.view(torch.int32)
+    ordered = bits ^ ((bits >> 31) & 0x7FFFFFFF)  # monotone in the float value (sign-magnitude -> two's complement)
+    L = flat.shape[1]  # scores are [E, a, n]: flat index -> (index // n, index % n)
+    low = (L - 1) - torch.arange(L, device=s.device, dtype=torch.int64)
+    keys = (ordered.to(torch.int64) << 32) + low
+    top = torch.topk(keys, n_crosses, dim=1, largest=True, sorted=True).values
+    idx = (L - 1) - (top & 0xFFFFFFFF)
+    vals = torch.gather(flat, 1, idx)
     reps = torch.ceil(torch.softmax(vals, dim=1) * n_crosses).to(torch.int64)
     ends = torch.cumsum(reps, dim=1)  # pair b fills output slots [ends[b-1], ends[b])
     slots = torch.arange(n_crosses, device=s.device).expand(E, n_crosses).contiguous()

@@ -447,3 +447,26 @@ def test_selection_scores_device_index_math_equals_host(cuda_device, k, n_crosse
         dev = env._convert_actions_device(scores, key).cpu().numpy()
         assert dev.shape == (num_envs, n, 2) and dev.dtype == np.int32
         assert np.array_equal(dev, host)
+
+
+def test_vec_reseed_mid_episode_discards_lookahead_masks(cuda_device):
+    """The masks of the next two steps are generated ahead of time from the key chain; `reset(seed=...)` in the middle of
+    an episode changes the chain, so those masks must be dropped (slot lookup is by key) and the trajectory must equal a
+    fresh env's under the new seed."""
+    num_envs, n = 33, 50  # 33 envs: the fused step kernel with mask rows staged in shared memory
+    env = gym().make("VecBreedGym", num_envs=num_envs, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n)
+    germ = np.load(GENOME)
+    rng = np.random.default_rng(5)
+    env.reset(seed=1)
+    for _ in range(3):
+        env.step(rng.integers(0, n, (num_envs, n, 2)))
+    pop, infos = env.reset(seed=9)
+    osim = oracle_sim(env.simulator, 9)
+    _, opops, _ = cr.vec_reset(germ, n, num_envs, jp.key(9), "legacy")
+    assert np.array_equal(np.asarray(pop), opops)
+    for _ in range(4):
+        action = rng.integers(0, n, (num_envs, n, 2))
+        pop, rews, ter, tru, infos = env.step(action)
+        opops = cr.vec_step(osim, opops, action)
+        assert np.array_equal(np.asarray(pop), opops)
+        assert np.allclose(infos["GEBV"], cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)

@@ -125,6 +125,9 @@ def test_pair_scores_conversion_matches_per_env_composition():
     n = 12
     sc = rng.standard_normal((3, n, n)).astype(np.float32)
     sc[1, 2, 3] = sc[1, 0, 0] = sc[1].max() + 1  # a tie for the top pair: lower flat index first
+    sc[2, 5:9, :] = 0.0
+    sc[2, 6, 1:4] = -0.0  # -0.0 == +0.0: still ordered by flat index
+    sc[2, 0, :] = -1.5    # negative ties
     got = _pairs_from_scores(torch.from_numpy(sc), n, "cpu").numpy()
     for e in range(3):
         v, i = jp.top_k(sc[e].reshape(-1), n)
