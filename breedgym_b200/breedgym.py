@@ -102,8 +102,11 @@ class BreedGym(Env):
         action = np.asarray(action)
         if action.ndim != 2 or action.shape[1] != 2:
             raise ValueError(f"action must have shape (n, 2), got {action.shape}")
-        parents = self.population[action]  # lazy n x 2 x markers x 2 view
-        self.population = self.simulator.cross(parents)
+        # `parents = self.population[action]; self.simulator.cross(parents)` and the GEBV of the offspring
+        # (breedgym/breedgym.py:142-143, 233) in one library call
+        self.population, gebv = self.simulator.cross_and_score(self.simulator.as_packed(self.population), action)
+        self._GEBV = self.simulator._gebv_frame(gebv)
+        self._GEBV_cache = True
         self.step_idx += 1
         self._update_spaces()
 
