@@ -64,7 +64,8 @@ def config_dict(n_gpus, replicas=REPLICAS):
         "num_generations": NUM_GENERATIONS,
         "parallelism": f"env-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
         "l2": f"inputs larger than L2: {REPLICAS} independent replicas stepped round-robin "
-              f"({REPLICAS} x 120 MB of populations between reuse, L2 = 126 MB); per-kernel breakdown: 256 MiB flush",
+              f"({REPLICAS} x {2 * ENVS_PER_GPU * N_IND * 2560 / 1e6:.0f} MB of populations between reuse, L2 = 126 MB); "
+              f"per-kernel breakdown: 256 MiB flush",
         "observation": "packed bit planes resident in HBM (bool observation materialised on request only)",
         "rng": "threefry2x32 legacy layout, key schedule S2, seed 7",
     }
@@ -487,7 +488,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", type=int, default=REPLICAS, help="independent workload copies stepped round-robin")
     ap.add_argument("--skip-e2e", action="store_true", help="diagnostics: only the device-resident value")
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU,
+                    help="envs per GPU (default 64 = BASELINE config C2; 512 = one GPU's share of C5, 4096 envs on 8 GPUs)")
     args = ap.parse_args()
+    if args.envs_per_gpu != ENVS_PER_GPU:
+        globals()["ENVS_PER_GPU"] = args.envs_per_gpu
+        globals()["WORKLOAD"] = WORKLOAD.replace("C2 vector env: 64 envs/GPU", f"vector env: {args.envs_per_gpu} envs/GPU")
+        if args.replicas == REPLICAS and args.envs_per_gpu >= 256:
+            args.replicas = 1  # one population pair already exceeds L2
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
