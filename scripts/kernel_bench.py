@@ -28,6 +28,7 @@ CONFIGS = {
     "C2": (64, 370, 10_000, 1),
     "C3": (1, 1000, 100_002, 1),
     "C4s": (1, 2000, 1_000_000, 16),   # C4 scaled to 2k offspring (same kernels, same row shape)
+    "C4": (1, 10_000, 1_000_000, 16),  # BASELINE config 4 at full size: 10k offspring of 1000 parents x 1M markers, 16 traits
     "C5": (512, 370, 10_000, 1),       # one GPU's share of 4096 envs / 8
 }
 
@@ -60,7 +61,7 @@ def main():
         sim = Simulator(genetic_map=df, device=0, seed=0, rng_layout=args.layout)
     lib = _lib.load()
     Wpad = sim.words_per_row
-    n_src = n if args.config != "C4s" else 1000
+    n_src = n if args.config not in ("C4s", "C4") else 1000
     lead = (E, n_src) if E > 1 else (n_src,)
     pop = torch.randint(-2**31, 2**31 - 1, (*lead, 2, Wpad), dtype=torch.int32, device=dev)
     tail = m % 32
