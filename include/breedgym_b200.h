@@ -116,8 +116,8 @@ int bg_cross(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32
  * (vector env) the two run as ONE kernel (cross_gebv.cu): the parents' bit planes are gathered into
  * shared memory, the offspring words are stored once and scored on the tensor cores before they
  * leave the SM (breedgym/vector/vec_env.py:89-94: cross, then get_info's GEBV_model(populations)).
- * With mutation > 0 or more than 8 traits per 64 digit columns of tensor memory it falls back to
- * bg_cross + bg_gebv; BG_NO_FUSE=1 in the environment forces that path (cross-checks). */
+ * With mutation > 0 or more than 32 traits it falls back to bg_cross + bg_gebv; BG_NO_FUSE=1 in
+ * the environment forces that path (cross-checks). */
 int bg_cross_gebv(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src,
                   int64_t n, const uint32_t cross_key[2], int layout, int schedule, float *gebv_out, void *stream);
 
