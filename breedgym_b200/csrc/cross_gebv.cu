@@ -436,7 +436,7 @@ bool bg_cross_gebv_fused_ok(const bg_engine *eng, int64_t E, int64_t n_src, int6
     const size_t smem = (size_t)XG_R * (XG_IN_BYTES + XG_MASK_BYTES) + (size_t)2 * 2 * N * STEP_K;
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
-    if (smem > (size_t)eng->max_smem_optin || d_cols + XG_S * (STEP_K / 4) > 512) return false;
+    if (smem + 4096 > (size_t)eng->max_smem_optin || d_cols + XG_S * (STEP_K / 4) > 512) return false;  // + the static arrays
     if (eng->tc_steps % XG_SPS != 0 || E * n >= (int64_t(1) << 31)) return false;
     return (int64_t)eng->Wpad / 4 * 2 * (n_src > n ? n_src : n) * E < (int64_t(1) << 32);
 }
@@ -463,7 +463,7 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
     if (nbp > XG_BP_MAX) nbp = XG_BP_MAX;
     if (nbp < 2) nbp = 2;
     const size_t smem = rings + (size_t)nbp * 2 * b_bytes;
-    BG_REQUIRE(smem <= (size_t)eng->max_smem_optin, BG_ELIMIT, "too many traits for the fused cross+GEBV tile");
+    BG_REQUIRE(smem + 4096 <= (size_t)eng->max_smem_optin, BG_ELIMIT, "too many traits for the fused cross+GEBV tile");
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
     uint32_t tcols = 32;

@@ -420,7 +420,7 @@ def test_full_size_vector_step_sampled_rows_and_properties(cuda_device):
 
 @pytest.mark.parametrize("m,T,E,n_src,n", [(10000, 1, 5, 37, 41), (333, 3, 3, 20, 130), (100002, 1, 2, 9, 7), (4099, 16, 4, 12, 64),
                                            (10000, 1, 64, 20, 25), (1000, 2, 32, 10, 13), (777, 1, 40, 7, 9), (2049, 1, 128, 5, 3),
-                                           (4097, 4, 17, 6, 33)])
+                                           (4097, 4, 17, 6, 33), (300, 24, 2, 6, 10), (257, 32, 3, 5, 9)])
 def test_fused_cross_gebv_equals_cross_then_gebv(cuda_device, m, T, E, n_src, n):
     """bg_cross_gebv (one fused kernel for E > 1) == bg_cross followed by bg_gebv, bit for bit, and == the oracle."""
     import torch
