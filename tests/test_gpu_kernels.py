@@ -515,3 +515,48 @@ def test_million_marker_multi_trait_c4_shape(cuda_device):
     assert np.allclose(gebv, cr.gebv(got, sim.GEBV_model.marker_effects), rtol=GEBV_RTOL, atol=0)
     assert np.array_equal(gebv, gebv_algo(sim, out, 4))  # both tensor-core variants agree bit for bit
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("m,T,E,n", [(10000, 1, 64, 370), (10000, 1, 512, 370), (4000, 2, 200, 90)])
+def test_fused_step_kernel_full_size_equals_two_kernel_path(cuda_device, m, T, E, n):
+    """BASELINE configs C2 (64 envs x 370 x 10 000) and one GPU's share of C5 (512 envs): the fused cross + GEBV kernel
+    against the blend + GEBV kernels (themselves checked against the oracle above), bit for bit, on random packed
+    populations generated on the GPU; plus the property that every offspring allele comes from its parent."""
+    import os
+
+    import torch
+
+    from breedgym_b200 import _lib
+
+    sim = make_sim(make_map(m, n_chr=10, T=T, seed=5))
+    W = sim.words_per_row
+    g = torch.Generator(device=cuda_device).manual_seed(E + n)
+    pop = torch.randint(-2**31, 2**31 - 1, (E, n, 2, W), dtype=torch.int32, device=cuda_device, generator=g)
+    full, tail = m // 32, m % 32
+    pop[..., full + (1 if tail else 0):] = 0  # padding bits are zero in a real population
+    if tail:
+        pop[..., full] &= (1 << tail) - 1
+    acts = torch.randint(0, n, (E, n, 2), dtype=torch.int32, device=cuda_device, generator=g)
+    key = jp.key(99)
+    outs, gebvs = [], []
+    for no_fuse in (False, True):
+        out = torch.zeros((E, n, 2, W), dtype=torch.int32, device=cuda_device)
+        gebv = torch.zeros((E, n, T), dtype=torch.float32, device=cuda_device)
+        if no_fuse:
+            os.environ["BG_NO_FUSE"] = "1"
+        try:
+            _lib.check(_lib.load().bg_cross_gebv(sim._engine, pop.data_ptr(), acts.data_ptr(), out.data_ptr(), E, n, n,
+                                                 _lib.nptr(key), sim._layout(), sim._schedule(), gebv.data_ptr(), sim._stream()))
+        finally:
+            os.environ.pop("BG_NO_FUSE", None)
+        outs.append(out)
+        gebvs.append(gebv)
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(gebvs[0], gebvs[1])
+    # allele provenance on one env: offspring plane p only holds bits present in one of parent p's two planes
+    e = E // 3
+    par = pop[e][acts[e].long()]  # [n, 2 (which parent), 2 (plane), W]
+    child = outs[0][e]            # [n, 2 (plane = which parent's gamete), W]
+    for p in range(2):
+        c, h0, h1 = child[:, p], par[:, p, 0], par[:, p, 1]
+        assert bool(torch.all((c & ~(h0 | h1)) == 0)) and bool(torch.all((~c & (h0 & h1)) == 0))
