@@ -83,6 +83,8 @@ class VecBreedGym(VectorEnv):
         self._h2d_done = None
         self._vec_step_fn = _lib.load().bg_vec_step
         self._germ_gebv = None
+        self._prefetched = None
+        self._side = None
 
     def _set_spaces(self):
         n, m = self.individual_per_gen, self.germplasm.shape[1]
@@ -238,28 +240,79 @@ class VecBreedGym(VectorEnv):
         sim, E, n = self.simulator, self.num_envs, self.individual_per_gen
         T = sim.GEBV_model.n_traits
         key = np.ascontiguousarray(self.random_key, dtype=np.uint32)
-        idx = torch.empty((E, n), dtype=torch.int32, device=self.device)
-        words = sim._empty_words(E, n)
-        germ = self.germplasm.words.contiguous()
         if self._germ_gebv is None and not os.environ.get("BG_NO_GERM_GEBV"):  # once: the reset infos are gathered from the germplasm's GEBVs
             self._germ_gebv = sim._gebv(self.germplasm).to(torch.float32).contiguous()  # raw kernel output, as bg_vec_reset computes
         host_info = self.info_device == "host"
-        if host_info:
-            io = self._host_io((E, n, 2), T)
-            gebv_dev_ptr, gebv_host_ptr = io["gebv_dev"], io["gebv_pin"]
+        pre, self._prefetched = self._prefetched, None
+        if pre is not None and np.array_equal(pre["key"], key) and pre["n"] == n:
+            # this reset was drawn ahead of time on the side stream (see _prefetch_reset): adopt its buffers
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(pre["event"])
+            idx, words, gebv_dev = pre["idx"], pre["words"], pre["gebv_dev"]
+            for t in (idx, words, gebv_dev):
+                t.record_stream(main)
+            if host_info:
+                pre["event"].synchronize()
+                infos_gebv = pre["gebv_pin"].numpy().copy()
+            else:
+                infos_gebv = gebv_dev
         else:
-            gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
-            gebv_dev_ptr, gebv_host_ptr = gebv_dev.data_ptr(), None
-        # env g draws permutation(keys[1 + g], N)[:n] with keys = split(random_key, total + 1); one C call does
-        # the draw, the gather from the germplasm and the reset infos
-        _lib.check(_lib.load().bg_vec_reset(sim._engine, germ.data_ptr(), germ.shape[0], _lib.nptr(key), total, begin, E, n,
-                                            sim._layout_id, idx.data_ptr(), words.data_ptr(), gebv_dev_ptr, gebv_host_ptr,
-                                            self._germ_gebv.data_ptr() if self._germ_gebv is not None else None, sim._stream()))
+            idx = torch.empty((E, n), dtype=torch.int32, device=self.device)
+            words = sim._empty_words(E, n)
+            germ = self.germplasm.words.contiguous()
+            if host_info:
+                io = self._host_io((E, n, 2), T)
+                gebv_dev_ptr, gebv_host_ptr = io["gebv_dev"], io["gebv_pin"]
+            else:
+                gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
+                gebv_dev_ptr, gebv_host_ptr = gebv_dev.data_ptr(), None
+            # env g draws permutation(keys[1 + g], N)[:n] with keys = split(random_key, total + 1); one C call does
+            # the draw, the gather from the germplasm and the reset infos
+            _lib.check(_lib.load().bg_vec_reset(sim._engine, germ.data_ptr(), germ.shape[0], _lib.nptr(key), total, begin, E, n,
+                                                sim._layout_id, idx.data_ptr(), words.data_ptr(), gebv_dev_ptr, gebv_host_ptr,
+                                                self._germ_gebv.data_ptr() if self._germ_gebv is not None else None, sim._stream()))
+            infos_gebv = io["gebv_np"].copy() if host_info else gebv_dev
         self.random_key = _lib.key_split_at(self.random_key, 0, total + 1, sim.rng_layout)
         self._reset_indices = idx
         self.populations = PackedPopulation(sim, words)
-        self.reset_infos = {"GEBV": io["gebv_np"].copy() if host_info else gebv_dev}
+        self.reset_infos = {"GEBV": infos_gebv}
+        # (device mode only: with host infos the step is host-bound and the extra stream / event bookkeeping of the
+        #  prefetch costs more host time than the reset kernels it hides: 640 k -> 580 k env-steps/s end to end)
+        if (self.autoreset and self.info_device == "device" and self._germ_gebv is not None
+                and not os.environ.get("BG_NO_RESET_PREFETCH")):
+            self._prefetch_reset()
         return self.populations, self.reset_infos
+
+    def _prefetch_reset(self):
+        """Draw the NEXT reset now, on a side stream, while the episode runs: it depends on `random_key` and the
+        germplasm only (vec_env.py:109-130), so at the end of the episode the autoreset adopts finished buffers instead
+        of running the permutation + gather (+ copy of the infos) on the step's critical path.  A reset with a seed, other
+        options or a `random_key` somebody changed in between simply ignores it."""
+        sim, E, n = self.simulator, self.num_envs, self.individual_per_gen
+        begin, total = self.env_shard
+        T = sim.GEBV_model.n_traits
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        key = np.array(self.random_key, dtype=np.uint32, copy=True)
+        germ = self.germplasm.words.contiguous()
+        host_info = self.info_device == "host"
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._side):
+            self._side.wait_stream(main)  # (the germplasm GEBVs may have been computed just now on the main stream)
+            idx = torch.empty((E, n), dtype=torch.int32, device=self.device)
+            words = sim._empty_words(E, n)
+            gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.load().bg_vec_reset(sim._engine, germ.data_ptr(), germ.shape[0], _lib.nptr(key), total, begin, E, n,
+                                                sim._layout_id, idx.data_ptr(), words.data_ptr(), gebv_dev.data_ptr(), None,
+                                                self._germ_gebv.data_ptr(), ctypes.c_void_p(self._side.cuda_stream)))
+            gebv_pin = None
+            if host_info:
+                gebv_pin = self._pinned_buf("reset_gebv", (E, n, T), torch.float32)
+                gebv_pin.copy_(gebv_dev, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(self._side)
+        self._prefetched = {"key": key, "n": n, "idx": idx, "words": words, "gebv_dev": gebv_dev, "gebv_pin": gebv_pin,
+                            "event": event}
 
     def get_info(self) -> dict:
         gebv = self.simulator.GEBV_model(self.populations)

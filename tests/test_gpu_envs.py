@@ -470,3 +470,31 @@ def test_vec_reseed_mid_episode_discards_lookahead_masks(cuda_device):
         opops = cr.vec_step(osim, opops, action)
         assert np.array_equal(np.asarray(pop), opops)
         assert np.allclose(infos["GEBV"], cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)
+
+
+def test_vec_device_mode_prefetched_autoreset_matches_oracle(cuda_device):
+    """info_device="device": the next reset is drawn ahead of time on a side stream and adopted at the autoreset; the
+    trajectory across two autoresets must equal the oracle's, and a reseed must discard the prefetched draw."""
+    import torch
+
+    num_envs, n = 3, 60
+    env = gym().make("VecBreedGym", num_envs=num_envs, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n,
+                     num_generations=3, info_device="device")
+    germ = np.load(GENOME)
+    rng = np.random.default_rng(2)
+    for seed in (7, 8):
+        pop, infos = env.reset(seed=seed)
+        assert env._prefetched is not None
+        osim = oracle_sim(env.simulator, seed)
+        okey, opops, _ = cr.vec_reset(germ, n, num_envs, jp.key(seed), "legacy")
+        assert np.array_equal(np.asarray(pop), opops)
+        for step in range(7):
+            action = rng.integers(0, n, (num_envs, n, 2))
+            pop, rews, ter, tru, infos = env.step(torch.from_numpy(action).to(cuda_device))
+            opops = cr.vec_step(osim, opops, action)
+            assert np.allclose(infos["GEBV"].cpu().numpy(), cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)
+            if step % 3 == 2:  # autoreset: the returned population is the next episode's first
+                assert bool(np.all(tru))
+                okey, opops, _ = cr.vec_reset(germ, n, num_envs, okey, "legacy")
+                assert np.allclose(env.reset_infos["GEBV"].cpu().numpy(), cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)
+            assert np.array_equal(np.asarray(pop), opops)
