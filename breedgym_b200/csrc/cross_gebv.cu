@@ -17,19 +17,28 @@
 //                             with the row, so the one-row-per-lane reads below are conflict free).  Nothing
 //                             waits on a scoreboard: completion lands on an mbarrier
 //                             (cp.async.mbarrier.arrive.noinc), so the bytes in flight are bounded by the ring
-//                             (2 x 32 KB per CTA, 2 CTAs per SM), not by registers.  Threads 0-63 also stage the
-//                             mask rows of the tile's (<= 8) children.
+//                             (3 x 32 KB per CTA, 2 CTAs per SM), not by registers.  Threads 0-63 also stage the
+//                             mask rows of the tile's (<= 8) children.  Before a ring slot is gathered into again,
+//                             the same warps drain the offspring words the expanders left in it to HBM, four lanes
+//                             per 64-byte row segment (coalesced 128-bit stores).
 //   warps 0-7  (expanders)  : thread t <-> offspring t of the tile <-> TMEM lane t; the two groups of 4 warps take
 //                             alternate steps.  4 x ld.shared.v4 + the two mask quads (broadcast ld.shared; with
 //                             few envs per-lane ld.global.nc, prefetched a step ahead), one LOP3 per word selects
 //                             the alleles (h0 & ~M | h1 & M), the offspring words replace parent A's IN PLACE in
 //                             the stage (the loader warps store them from there), then 4 words per plane ->
 //                             128 prescaled dosage bytes -> tcgen05.st into the A stage in tensor memory.
-//                             Before a ring slot is gathered into again, the same warps drain the offspring
-//                             words the expanders left in it to HBM, four lanes per 64-byte row segment.
-//   warp 8     (digits)     : 1-D bulk copies (TMA) of the digit tiles, 4 steps per copy, two halves in flight.
-//   warp 9     (MMA)        : tcgen05.mma.kind::i8, A from TMEM, B from shared memory, D in TMEM.
-//   warps 0-3  (epilogue)   : digits -> int64 -> K-split atomics -> float32 (tc_common.cuh).
+//   warp 8     (digits)     : 1-D bulk copies (TMA) of the digit tiles, one per pair of steps, after an L2 prefetch
+//                             of the CTA's whole digit range.
+//   warp 9     (MMA)        : tcgen05.mma.kind::i8, A from TMEM, B from shared memory, D in TMEM; the whole warp runs
+//                             the loop and one elected lane issues (elect.sync), one barrier round and one
+//                             tcgen05.commit per PAIR of steps.
+//   warps 0-3  (epilogue)   : digits -> int64 -> one 64-bit atomic per value carrying the K-split partial sum and
+//                             the arrival count -> float32 by the last arrival (tc_common.cuh).
+//
+// The kernel is capped at 64 registers per thread (launch bounds of 512 threads, 448 launched): two CTAs then leave
+// 8192 registers of the SM free, exactly one 128-thread CTA of the mask kernel of the NEXT steps (meiosis.cu, side
+// stream), which runs in the issue slots this latency-bound kernel leaves idle.  Measured history and dead ends:
+// DESIGN.md section 4; `-DXG_TRACE=1` + scripts/fused_trace.py print one CTA's pipeline timeline.
 #include <cuda.h>
 #include <string.h>
 
