@@ -103,6 +103,7 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
                                int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st);
 
 // layout.cu
+int bg_launch_copy_mapped(const void *src, void *dst, size_t bytes, cudaStream_t st);
 int bg_launch_pack(const uint8_t *in, uint32_t *out, int64_t rows, int64_t m, int W, int Wpad, cudaStream_t st);
 int bg_launch_unpack(const uint32_t *in, uint8_t *out, int64_t rows, int64_t m, int Wpad, cudaStream_t st);
 int bg_launch_gather(const uint32_t *src, const int32_t *idx, uint32_t *dst, int64_t E, int64_t n_src, int64_t n,

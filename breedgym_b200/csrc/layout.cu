@@ -113,7 +113,31 @@ __global__ void __launch_bounds__(256) reset_indices_kernel(uint32_t k0, uint32_
     for (int j = tid; j < n; j += NT) idx_out[e * n + j] = x[j];
 }
 
+// 16-byte-wide copy between device memory and MAPPED pinned host memory (zero-copy over PCIe).  For the few hundred KB
+// the host-facing step moves, a kernel that reads / writes the pinned buffer directly costs less than a copy-engine
+// transfer (189 KB H2D: 18.5 us event to event through cudaMemcpyAsync).
+__global__ void __launch_bounds__(256) copy16_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int64_t n16,
+                                                     const uint32_t *__restrict__ src_tail, uint32_t *__restrict__ dst_tail, int ntail)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n16) dst[i] = src[i];
+    if (i < ntail) dst_tail[i] = src_tail[i];
+}
+
 }  // namespace
+
+// bytes % 4 == 0, both pointers 16-byte aligned and device-accessible
+int bg_launch_copy_mapped(const void *src, void *dst, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return BG_OK;
+    const int64_t n16 = (int64_t)(bytes / 16);
+    const int ntail = (int)((bytes % 16) / 4);
+    const int64_t threads = n16 > ntail ? n16 : ntail;
+    copy16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const uint4 *)src, (uint4 *)dst, n16,
+                                                                     (const uint32_t *)src + 4 * n16, (uint32_t *)dst + 4 * n16, ntail);
+    BG_LAUNCHED();
+    return BG_OK;
+}
 
 int bg_launch_pack(const uint8_t *in, uint32_t *out, int64_t rows, int64_t m, int W, int Wpad, cudaStream_t st)
 {

@@ -249,8 +249,6 @@ class VecBreedGym(VectorEnv):
             main = torch.cuda.current_stream(self.device)
             main.wait_event(pre["event"])
             idx, words, gebv_dev = pre["idx"], pre["words"], pre["gebv_dev"]
-            for t in (idx, words, gebv_dev):
-                t.record_stream(main)
             if host_info:
                 pre["event"].synchronize()
                 infos_gebv = pre["gebv_pin"].numpy().copy()
@@ -276,10 +274,12 @@ class VecBreedGym(VectorEnv):
         self._reset_indices = idx
         self.populations = PackedPopulation(sim, words)
         self.reset_infos = {"GEBV": infos_gebv}
-        # (device mode only: with host infos the step is host-bound and the extra stream / event bookkeeping of the
-        #  prefetch costs more host time than the reset kernels it hides: 640 k -> 580 k env-steps/s end to end)
+        # Opt-in experiment (BG_RESET_PREFETCH=1, device mode): draw the next reset ahead of time on a side stream.
+        # +5 % env-steps/s when it works, but runs at half speed now and then (the caching allocator and the second
+        # stream do not get along: 4 of 6 runs), so it is off by default; with host infos its stream / event
+        # bookkeeping costs more host time than the reset kernels it hides (640 k -> 580 k env-steps/s end to end).
         if (self.autoreset and self.info_device == "device" and self._germ_gebv is not None
-                and not os.environ.get("BG_NO_RESET_PREFETCH")):
+                and os.environ.get("BG_RESET_PREFETCH")):
             self._prefetch_reset()
         return self.populations, self.reset_infos
 
@@ -297,20 +297,25 @@ class VecBreedGym(VectorEnv):
         germ = self.germplasm.words.contiguous()
         host_info = self.info_device == "host"
         main = torch.cuda.current_stream(self.device)
-        with torch.cuda.stream(self._side):
-            self._side.wait_stream(main)  # (the germplasm GEBVs may have been computed just now on the main stream)
-            idx = torch.empty((E, n), dtype=torch.int32, device=self.device)
-            words = sim._empty_words(E, n)
-            gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
-            _lib.check(_lib.load().bg_vec_reset(sim._engine, germ.data_ptr(), germ.shape[0], _lib.nptr(key), total, begin, E, n,
-                                                sim._layout_id, idx.data_ptr(), words.data_ptr(), gebv_dev.data_ptr(), None,
-                                                self._germ_gebv.data_ptr(), ctypes.c_void_p(self._side.cuda_stream)))
-            gebv_pin = None
-            if host_info:
-                gebv_pin = self._pinned_buf("reset_gebv", (E, n, T), torch.float32)
+        # buffers from the MAIN stream's pool (the pool every step allocates its 60 MB population from), handed to the
+        # side stream with record_stream: allocating them under the side stream made the caching allocator fall back
+        # to synchronising cudaMalloc / cudaFree now and then (whole runs at 0.75 M instead of 1.36 M env-steps/s)
+        idx = torch.empty((E, n), dtype=torch.int32, device=self.device)
+        words = sim._empty_words(E, n)
+        gebv_dev = torch.empty((E, n, T), dtype=torch.float32, device=self.device)
+        for t in (idx, words, gebv_dev):
+            t.record_stream(self._side)
+        self._side.wait_stream(main)  # the buffers' previous users, and the germplasm GEBVs computed on the main stream
+        _lib.check(_lib.load().bg_vec_reset(sim._engine, germ.data_ptr(), germ.shape[0], _lib.nptr(key), total, begin, E, n,
+                                            sim._layout_id, idx.data_ptr(), words.data_ptr(), gebv_dev.data_ptr(), None,
+                                            self._germ_gebv.data_ptr(), ctypes.c_void_p(self._side.cuda_stream)))
+        gebv_pin = None
+        if host_info:
+            gebv_pin = self._pinned_buf("reset_gebv", (E, n, T), torch.float32)
+            with torch.cuda.stream(self._side):
                 gebv_pin.copy_(gebv_dev, non_blocking=True)
-            event = torch.cuda.Event()
-            event.record(self._side)
+        event = torch.cuda.Event()
+        event.record(self._side)
         self._prefetched = {"key": key, "n": n, "idx": idx, "words": words, "gebv_dev": gebv_dev, "gebv_pin": gebv_pin,
                             "event": event}
 

@@ -472,10 +472,13 @@ def test_vec_reseed_mid_episode_discards_lookahead_masks(cuda_device):
         assert np.allclose(infos["GEBV"], cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)
 
 
-def test_vec_device_mode_prefetched_autoreset_matches_oracle(cuda_device):
-    """info_device="device": the next reset is drawn ahead of time on a side stream and adopted at the autoreset; the
-    trajectory across two autoresets must equal the oracle's, and a reseed must discard the prefetched draw."""
+def test_vec_device_mode_prefetched_autoreset_matches_oracle(cuda_device, monkeypatch):
+    """info_device="device" with BG_RESET_PREFETCH=1 (opt-in): the next reset is drawn ahead of time on a side stream and
+    adopted at the autoreset; the trajectory across two autoresets must equal the oracle's, and a reseed must discard
+    the prefetched draw."""
     import torch
+
+    monkeypatch.setenv("BG_RESET_PREFETCH", "1")
 
     num_envs, n = 3, 60
     env = gym().make("VecBreedGym", num_envs=num_envs, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n,
