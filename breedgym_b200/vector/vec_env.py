@@ -34,6 +34,7 @@ from ..simulator import Simulator
 from ..utils.paths import DATA_PATH
 
 GENOME_FILE = DATA_PATH.joinpath("small_geno.npy")
+_SIDE_STREAMS = {}  # device index -> the process-wide side stream of the reset prefetch
 
 
 class VecBreedGym(VectorEnv):
@@ -275,8 +276,8 @@ class VecBreedGym(VectorEnv):
         self.populations = PackedPopulation(sim, words)
         self.reset_infos = {"GEBV": infos_gebv}
         # Opt-in experiment (BG_RESET_PREFETCH=1, device mode): draw the next reset ahead of time on a side stream.
-        # +5 % env-steps/s when it works, but runs at half speed now and then (the caching allocator and the second
-        # stream do not get along: 4 of 6 runs), so it is off by default; with host infos its stream / event
+        # +5 % env-steps/s when it works, but whole runs at half speed now and then (4 of 6; cause not found: neither
+        # a shared side stream nor more hardware connections cure it), so it is off by default; with host infos its stream / event
         # bookkeeping costs more host time than the reset kernels it hides (640 k -> 580 k env-steps/s end to end).
         if (self.autoreset and self.info_device == "device" and self._germ_gebv is not None
                 and os.environ.get("BG_RESET_PREFETCH")):
@@ -292,7 +293,12 @@ class VecBreedGym(VectorEnv):
         begin, total = self.env_shard
         T = sim.GEBV_model.n_traits
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            # ONE side stream per device, shared by all envs of the process: every extra stream takes one of the (8 by
+            # default) hardware connections, and streams that have to share one serialise against each other
+            key_dev = (self.device.index if self.device.index is not None else torch.cuda.current_device())
+            if key_dev not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key_dev] = torch.cuda.Stream(device=self.device)
+            self._side = _SIDE_STREAMS[key_dev]
         key = np.array(self.random_key, dtype=np.uint32, copy=True)
         germ = self.germplasm.words.contiguous()
         host_info = self.info_device == "host"
