@@ -622,7 +622,8 @@ static int copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStrea
 
 static int copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st)
 {
-    if (void *dp = (bytes % 4 == 0 && bytes <= BG_MAPPED_COPY_MAX) ? mapped_device_pointer(dst_host) : nullptr)
+    static const size_t d2h_max = getenv("BG_MAPPED_D2H_MAX") ? (size_t)atoll(getenv("BG_MAPPED_D2H_MAX")) : BG_MAPPED_COPY_MAX;  // tuning
+    if (void *dp = (bytes % 4 == 0 && bytes <= d2h_max) ? mapped_device_pointer(dst_host) : nullptr)
         return bg_launch_copy_mapped(src_dev, dp, bytes, st);
     BG_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
     return BG_OK;
