@@ -240,7 +240,8 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
     BG_CUDA(cudaMemcpy(eng->d_thr, thr.data(), nthr * sizeof(uint32_t), cudaMemcpyHostToDevice));
 
     if (n_traits > 0) {
-        // fixed point: w_fix = rint(w * 2^s), s = largest shift with 2*sum|w| * 2^s < 2^55 (the tensor-core kernels
+        // fixed point: w_fix = rint(w * 2^s), s = largest shift with 2*sum|w| * 2^s < 2^54, so that any GEBV sum, rounding of
+        // the w_fix included (+ at most one unit per marker), stays below 2^55 in magnitude (the tensor-core kernels
         // sum 64x these integers, see the digit table below, and must stay inside int64)
         const size_t stride = (size_t)((eng->Wpad + 7) / 8) * 256;
         std::vector<long long> wfix(stride * n_traits, 0ll);
@@ -256,7 +257,7 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
             if (sum > 0.0) {
                 int ex;
                 frexp(2.0 * sum, &ex);  // 2*sum < 2^ex
-                s = 55 - ex;
+                s = 54 - ex;
                 if (s > 1000) s = 1000;
                 if (s < -1000) s = -1000;
             }
