@@ -5,17 +5,22 @@
 
 A "step" is one vector-env step of BASELINE.json's config[1] per GPU:
 64 envs x 370 individuals x 10 000 markers (small_genetic_map.txt, trait Yield),
-i.e. mask generation + blend of all envs (cross), GEBV of every offspring, the
-max-GEBV reward and the on-device autoreset on every 10th step.  N > 1 shards
-64 x N envs, 64 per GPU (weak scaling), one process per GPU; the only collective
-is the reward all-gather on episode ends.
+i.e. the fused cross + GEBV kernel over all envs (the crossover masks of the following
+steps are generated on a side stream), the max-GEBV reward and the on-device autoreset
+on every 10th step.  N > 1 shards 64 x N envs, 64 per GPU (weak scaling), one process
+per GPU; the only collective is the reward all-gather on episode ends (ncclAllGather
+through the C ABI, on the step's stream).
 
   value      env-steps/s, inputs resident in HBM, CUDA-event timed over the K steps; the working set
              (4 replicas of the workload, round-robin) is larger than L2
   e2e        the same through VecBreedGym.step with HOST actions in / GEBV+rewards out
   roofline   dominant kernel: algorithmic bytes / CUDA-event time vs measured HBM peak
-  cpu_baseline / --impl reference: the C oracle (OpenMP) on the host cores -- jax/chromax are
-             not installable on this image, so the oracle port stands in for the JAX-CPU path
+  cpu_baseline / --impl reference: the C oracle (OpenMP) on the host cores, drawing the crossover masks once per
+             step for all envs as the reference's vmap does -- jax/chromax are not installable on this image, so
+             the oracle port stands in for the JAX-CPU path
+  c5         BASELINE config[4]: 512 envs per GPU (weak) and 4096 envs in total (strong) records
+  configs    (N = 1) the other named shapes: C1 single env through the Gym API, C3 wheat-scale cross + GEBV,
+             C4 10 000 x 1 M markers cross + 16-trait GEBV, each with its own roofline and CPU baseline
 """
 from __future__ import annotations
 
@@ -52,19 +57,19 @@ def workload_inputs():
     return germ, data / "small_genetic_map.txt"
 
 
-def config_dict(n_gpus, replicas=REPLICAS):
-    REPLICAS = replicas  # noqa: N806 (shadow for the f-strings below)
+def config_dict(n_gpus, replicas=REPLICAS, envs_per_gpu=None, envs_total=None):
+    epg = ENVS_PER_GPU if envs_per_gpu is None else envs_per_gpu
     return {
         "workload": WORKLOAD,
-        "envs_total": ENVS_PER_GPU * n_gpus,
-        "envs_per_gpu": ENVS_PER_GPU,
+        "envs_total": epg * n_gpus if envs_total is None else envs_total,
+        "envs_per_gpu": epg,
         "individuals": N_IND,
         "markers": N_MARKERS,
         "traits": 1,
         "num_generations": NUM_GENERATIONS,
         "parallelism": f"env-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
-        "l2": f"inputs larger than L2: {REPLICAS} independent replicas stepped round-robin "
-              f"({REPLICAS} x {2 * ENVS_PER_GPU * N_IND * 2560 / 1e6:.0f} MB of populations between reuse, L2 = 126 MB); "
+        "l2": f"inputs larger than L2: {replicas} independent replicas stepped round-robin "
+              f"({replicas} x {2 * epg * N_IND * 2560 / 1e6:.0f} MB of populations between reuse, L2 = 126 MB); "
               f"per-kernel breakdown: 256 MiB flush",
         "observation": "packed bit planes resident in HBM (bool observation materialised on request only)",
         "rng": "threefry2x32 legacy layout, key schedule S2, seed 7",
@@ -74,8 +79,10 @@ def config_dict(n_gpus, replicas=REPLICAS):
 # --------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's C restatement on the host cores
 # --------------------------------------------------------------------------------------
-def cpu_steps(n_steps, warmup, envs=ENVS_PER_GPU, min_seconds=0.0):
-    """Times full vector-env steps (cross of all envs + GEBV + max reward) with the C oracle."""
+def cpu_steps(n_steps, warmup, envs=ENVS_PER_GPU, min_seconds=0.0, shared_masks=True):
+    """Times full vector-env steps (cross of all envs + GEBV + max reward) with the C oracle.  shared_masks: the 2n
+    crossover masks are drawn once per step and reused by every env (how the reference's vmap executes,
+    breedgym/vector/vec_env.py:75-77); False re-draws them per env (E x the Threefry work)."""
     from oracle import c_oracle as co
     from oracle import chromax_ref as cr
     from oracle import jax_prng as jp
@@ -95,7 +102,7 @@ def cpu_steps(n_steps, warmup, envs=ENVS_PER_GPU, min_seconds=0.0):
         ks = jp.split(key, 2)
         key, k = ks[0], ks[1]
         t0 = time.perf_counter()
-        pops = co.cross_envs(pops, act, r, k)
+        pops = co.cross_envs(pops, act, r, k, shared_masks=shared_masks)
         gebv = co.gebv(pops, eff)
         _ = gebv.max(axis=(1, 2))
         dt = time.perf_counter() - t0
@@ -109,32 +116,40 @@ def cpu_steps(n_steps, warmup, envs=ENVS_PER_GPU, min_seconds=0.0):
             "cores": co.num_threads(), "envs": envs}
 
 
+CPU_NOTE = ("jax/chromax are not installable on this image; the oracle's C restatement of the reference algorithm is timed "
+            "instead (masks drawn once per step for all envs, as the reference's vmap does)")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # bounded sample: every step processes `envs` of the 64 envs of a GPU's share, chosen so that the whole
-    # --steps K --warmup W run stays around a minute whatever K is (throughput per env-step does not depend on it)
+    # bounded sample: every step processes `envs` of the 64 envs of ONE GPU's share (rank 0 only, whatever --gpus is),
+    # chosen so that the whole --steps K --warmup W run stays around a minute (throughput per env-step barely depends
+    # on it: the per-step mask draw is amortised over fewer envs, which makes a smaller sample slightly pessimistic)
     calib = cpu_steps(1, 0, envs=8)
     per_env_step = 1.0 / calib["env_steps_per_sec"]
     budget_s = 60.0
     envs = int(max(1, min(ENVS_PER_GPU, budget_s / (per_env_step * max(1, args.steps + args.warmup)))))
     res = cpu_steps(args.steps, args.warmup, envs=envs)
-    sample = (f"{res['steps']} vector-env steps of {res['envs']} envs x {N_IND} x {N_MARKERS} each "
-              f"(cross + GEBV + reward), C oracle, OpenMP")
+    redraw = cpu_steps(1, 0, envs=min(envs, 8), shared_masks=False)
+    sample = (f"{res['steps']} vector-env steps of {res['envs']} envs x {N_IND} x {N_MARKERS} each (cross + GEBV + reward) "
+              f"on rank 0's host cores, C oracle with OpenMP, shared-mask port (2n masks drawn once per step)")
+    cfg = config_dict(1, envs_per_gpu=res["envs"])
+    cfg["parallelism"] = f"{res['cores']} host threads (CPU arm: runs on rank 0 only, --gpus {args.gpus} is ignored)"
+    cfg["l2"] = "n/a (CPU)"
     line = {
         "impl": "reference",
         "metric": METRIC, "value": res["env_steps_per_sec"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": res["steps"], "warmup": args.warmup,
         "ms_per_step": 1e3 * res["seconds"] / res["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 bit planes + int64 fixed point (CPU port: u8 + f64)", "data": "synthetic",
-        "config": config_dict(args.gpus),
+        "dtype": "u8 alleles + f64 GEBV (CPU port)", "data": "synthetic",
+        "config": cfg,
         "offspring_markers_per_sec": res["env_steps_per_sec"] * N_IND * N_MARKERS,
         "cpu_baseline": {"value": res["env_steps_per_sec"], "unit": UNIT, "cores": res["cores"], "kind": "port",
-                         "sample": sample,
-                         "note": "jax/chromax are not installable on this image; the oracle's C restatement "
-                                 "of the reference algorithm is timed instead"},
+                         "sample": sample, "note": CPU_NOTE,
+                         "per_env_redraw_value": redraw["env_steps_per_sec"]},
         "e2e": {"value": res["env_steps_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -213,14 +228,114 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
-def measured_peak_gbs():
+def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         try:
-            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            d = json.loads(p.read_text())
+            return d, "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1700.0}, "fallback (B200_PROFILING.md)"
+
+
+def measured_peak_gbs():
+    d, src = measured_peaks()
+    return float(d["hbm_gbs"]), src
+
+
+def int32_peak():
+    """Measured integer-pipe issue rate (scripts/int32_peak.cu -> profiles/int32_peak.json), for the Threefry-bound kernels."""
+    p = ROOT / "profiles" / "int32_peak.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            pass
+    return None
+
+
+def traffic_for(kernel, key):
+    """DRAM bytes per launch from the committed ncu capture of exactly this configuration, else None."""
+    prof = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(prof.read_text()).get(kernel, {}).get(key)
+    except Exception:
+        return None
+
+
+class Harness:
+    """Timing plumbing shared by the legs: barrier + synchronize on both sides, CUDA events on the launching stream,
+    max over ranks, SM clock spin-up, garbage collector parked."""
+
+    def __init__(self, torch, dist, dev, world):
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2(self):
+        self.flush_buf.fill_(1)
+
+    def spin_up(self, seconds=0.4):
+        """Keep the GPU busy long enough for the SM clock to leave its idle state before anything is timed."""
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(20):
+                self.flush_buf.fill_(0)
+            self.torch.cuda.synchronize()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps):
+        """`steps` calls bracketed by barrier + synchronize; returns (device seconds between two CUDA events, host
+        seconds spent enqueueing)."""
+        # a full (generation 2) Python garbage collection walks every object the imported packages hold: 40-500 ms,
+        # wherever it happens to fall.  Collect now and park the survivors so that none falls inside the timed region.
+        gc.collect()
+        gc.freeze()
+        torch = self.torch
+        stream = torch.cuda.current_stream(self.dev)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        start.record(stream)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(i)
+        host = time.perf_counter() - t0
+        end.record(stream)
+        self.barrier()
+        return start.elapsed_time(end) * 1e-3, host
+
+
+def vec_value_leg(h, make_env, acts_dev, K, W, replicas, sample_clocks=None):
+    """Device-resident step loop: `replicas` independent envs round-robin.  Warm-up runs every replica through a
+    whole episode (autoreset and the reward all-gather included) plus one untimed rehearsal of the K steps, so the
+    timed K steps carry the steady one-in-`num_generations` reset rate on warm code paths."""
+    envs = [make_env("device") for _ in range(replicas)]
+    n_act = len(acts_dev)
+
+    def step(i):
+        envs[i % replicas].step(acts_dev[i % n_act])
+
+    h.spin_up()
+    for i in range(max(W, replicas * (NUM_GENERATIONS + 1))):
+        step(i)
+    h.timed(step, K)
+    if sample_clocks is not None:
+        sample_clocks.start()
+    t_dev, t_host = h.timed(step, K)
+    clocks = sample_clocks.stop() if sample_clocks is not None else None
+    return envs, h.max_over_ranks(t_dev), t_host, clocks
 
 
 def run_ours(args):
@@ -228,8 +343,8 @@ def run_ours(args):
     import torch.distributed as dist
 
     from breedgym_b200 import _lib
-    from breedgym_b200.vector import VecBreedGym
-    from breedgym_b200.vector.sharded import allgather_rewards, shard_counts, shard_range
+    from breedgym_b200.vector import ShardedVecBreedGym, VecBreedGym
+    from breedgym_b200.vector.sharded import shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -241,96 +356,50 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    h = Harness(torch, dist, dev, world)
+    if args.stream_priority is not None:  # diagnostics: run everything on a stream of this priority
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=args.stream_priority))
 
-    total_envs = ENVS_PER_GPU * world
-    begin, count = shard_range(total_envs, world, rank)
-    counts = shard_counts(total_envs, world)
     germ, gmap = workload_inputs()
     lib = _lib.load()
     K, W = args.steps, max(args.warmup, 3)
-    REPLICAS = max(1, args.replicas)
+    replicas = max(1, args.replicas)
+    env_kw = dict(initial_population=germ, genetic_map=gmap, trait_names=["Yield"], individual_per_gen=N_IND,
+                  num_generations=NUM_GENERATIONS, device=local_rank)
 
-    def make_env(info_device):
-        env = VecBreedGym(num_envs=count, initial_population=germ, genetic_map=gmap, trait_names=["Yield"],
-                          individual_per_gen=N_IND, num_generations=NUM_GENERATIONS, device=local_rank,
-                          info_device=info_device, env_shard=(begin, total_envs))
-        env.reset(seed=7)
-        return env
+    def env_factory(total_envs):
+        def make_env(info_device):
+            if world > 1:  # one process per GPU, env-sharded; the reward all-gather goes through bg_allgather_f32
+                env = ShardedVecBreedGym(total_envs=total_envs, info_device=info_device, **env_kw)
+            else:
+                env = VecBreedGym(num_envs=total_envs, info_device=info_device, **env_kw)
+            env.reset(seed=7)
+            return env
+        return make_env
 
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    def actions(count, n_act, seed):
+        rng = np.random.default_rng(seed)
+        host = [rng.integers(0, N_IND, (count, N_IND, 2), dtype=np.int32) for _ in range(n_act)]
+        return host, [torch.from_numpy(a).to(dev) for a in host]
 
-    def flush_l2():
-        flush_buf.fill_(1)
-
-    def spin_up(seconds=0.4):
-        """Keep the GPU busy long enough for the SM clock to leave its idle state before anything is timed."""
-        t0 = time.perf_counter()
-        while time.perf_counter() - t0 < seconds:
-            for _ in range(20):
-                flush_buf.fill_(0)
-            torch.cuda.synchronize()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    rng = np.random.default_rng(1 + rank)
-    n_act = 16  # distinct action batches, cycled
-    acts_host = [rng.integers(0, N_IND, (count, N_IND, 2), dtype=np.int32) for _ in range(n_act)]
-    acts_dev = [torch.from_numpy(a).to(dev) for a in acts_host]
+    total_envs = ENVS_PER_GPU * world
+    begin, count = shard_range(total_envs, world, rank)
+    acts_host, acts_dev = actions(count, 16, 1 + rank)
 
     # ---------------- value: device-resident inputs, pipelined, inputs larger than L2 ----------------
-    # REPLICAS independent copies of the workload are stepped round-robin: between two steps of the
-    # same replica ~REPLICAS x 120 MB of other populations stream through the 126 MB L2, so every
-    # step reads its population from HBM without a flush kernel polluting the pipeline.
-    envs = [make_env("device") for _ in range(REPLICAS)]
-    env = envs[0]
-
-    def device_step(i):
-        _, rews, _, tru, _ = envs[i % REPLICAS].step(acts_dev[i % n_act])
-        if world > 1 and bool(tru[0]):
-            allgather_rewards(rews, counts)  # the one collective of the path (NCCL)
-
-    def timed(fn, steps):
-        """K steps bracketed by barrier + synchronize; device time between two CUDA events."""
-        # a full (generation 2) Python garbage collection walks every object the imported packages hold: 40-500 ms,
-        # once every few thousand steps, wherever it happens to fall (seen as one block 5-10x slower than the others).
-        # Collect now and park the survivors in the permanent generation so that none falls inside the timed region.
-        gc.collect()
-        gc.freeze()
-        stream = torch.cuda.current_stream(dev)
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        start.record(stream)
-        for i in range(steps):
-            fn(i)
-        end.record(stream)
-        barrier()
-        return start.elapsed_time(end) * 1e-3  # seconds
-
-    spin_up()
-    for i in range(max(W, REPLICAS)):
-        device_step(i)
-    # untimed dress rehearsal of the timed region: on a freshly provisioned box the first seconds of a process run with
-    # cold page / instruction caches on the host (enqueue 3x slower: the device loop turns host-bound)
-    timed(device_step, K)
     sampler = ClockSampler(local_rank)
     launches0 = lib.bg_kernel_launches()
-    sampler.start()
-    t_value = max_over_ranks(timed(device_step, K))
-    launches = lib.bg_kernel_launches() - launches0
-    clocks = sampler.stop()
+    envs, t_value, t_host, clocks = vec_value_leg(h, env_factory(total_envs), acts_dev, K, W, replicas, sampler)
+    launches_total = lib.bg_kernel_launches() - launches0
+    # launches inside the timed region: counted over one more pass of K steps
+    l0 = lib.bg_kernel_launches()
+    for i in range(K):
+        envs[i % replicas].step(acts_dev[i % 16])
+    torch.cuda.synchronize()
+    launches = lib.bg_kernel_launches() - l0
 
     # ---------------- per-kernel breakdown (same inputs, same flush policy) ----------------
+    env = envs[0].env if world > 1 else envs[0]
     sim = env.simulator
     pop_words = env.populations.words
     E = count
@@ -341,31 +410,31 @@ def run_ours(args):
     key = np.array([0, 12345], dtype=np.uint32)
     stream = torch.cuda.current_stream(dev)
     sptr = sim._stream()
-    # the step = meiosis_masks (side stream, one step ahead) + cross_gebv_fused; blend_envs / gebv are the two
-    # kernels of the unfused path (BG_NO_FUSE=1), timed for comparison
+    # the step = cross_gebv_fused (+ meiosis_masks on the side stream, one launch per 8 steps); blend_envs / gebv are
+    # the two kernels of the unfused path (option fuse=0), timed for comparison
     bk = {"meiosis_masks": 0.0, "cross_gebv_fused": 0.0, "blend_envs": 0.0, "gebv": 0.0}
-    reps = min(K, 50)
-    spin_up(0.2)
-    # masks of `key` land in one of the engine's slots here: the timed bg_cross_gebv calls launch the fused kernel only
+    reps = min(max(K, 20), 50)
+    h.spin_up(0.2)
+    # masks of `key` land in one of the engine's mask batches here: the timed bg_cross_gebv calls launch the fused kernel only
     _lib.check(lib.bg_cross_gebv(sim._engine, pop_words.data_ptr(), acts_dev[0].data_ptr(), out_words.data_ptr(), E, N_IND, N_IND,
                                  _lib.nptr(key), 0, 2, gebv_out.data_ptr(), sptr))
     for it in range(3 + reps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
-        flush_l2()
+        h.flush_l2()
         ev[0].record(stream)
         _lib.check(lib.bg_meiosis_masks(sim._engine, mask.data_ptr(), 2 * N_IND, _lib.nptr(key), 0, 2, sptr))
         ev[1].record(stream)
-        flush_l2()
+        h.flush_l2()
         ev[2].record(stream)
-        _lib.check(lib.bg_cross_gebv(sim._engine, pop_words.data_ptr(), acts_dev[it % n_act].data_ptr(), out_words.data_ptr(), E,
+        _lib.check(lib.bg_cross_gebv(sim._engine, pop_words.data_ptr(), acts_dev[it % 16].data_ptr(), out_words.data_ptr(), E,
                                      N_IND, N_IND, _lib.nptr(key), 0, 2, gebv_out.data_ptr(), sptr))
         ev[3].record(stream)
-        flush_l2()
+        h.flush_l2()
         ev[4].record(stream)
-        _lib.check(lib.bg_blend_envs(sim._engine, pop_words.data_ptr(), acts_dev[it % n_act].data_ptr(), mask.data_ptr(),
+        _lib.check(lib.bg_blend_envs(sim._engine, pop_words.data_ptr(), acts_dev[it % 16].data_ptr(), mask.data_ptr(),
                                      None, out_words.data_ptr(), E, N_IND, N_IND, sptr))
         ev[5].record(stream)
-        flush_l2()
+        h.flush_l2()
         ev[6].record(stream)
         _lib.check(lib.bg_gebv(sim._engine, out_words.data_ptr(), E * N_IND, gebv_out.data_ptr(), sptr))
         ev[7].record(stream)
@@ -387,35 +456,38 @@ def run_ours(args):
                       "achieved_gbs": (alg[k] / (ms * 1e-3) / 1e9) if alg[k] else None}
         if alg[k]:
             kernels[k]["frac_of_hbm_peak"] = kernels[k]["achieved_gbs"] / peak
+    ip = int32_peak()
+    if ip:  # Threefry-bound: 2 * rows * ceil(m / 2) blocks... reported as draws/s against the measured integer issue rate
+        draws = 2 * N_IND * N_MARKERS
+        kernels["meiosis_masks"]["gdraws_per_s"] = draws / (bk["meiosis_masks"] * 1e-3) / 1e9
+        kernels["meiosis_masks"]["int_ops_per_draw"] = ip.get("threefry_int_ops_per_draw")
+        if ip.get("int32_gops") and ip.get("threefry_int_ops_per_draw"):
+            kernels["meiosis_masks"]["frac_of_int32_peak"] = (kernels["meiosis_masks"]["gdraws_per_s"] * ip["threefry_int_ops_per_draw"]
+                                                              / ip["int32_gops"])
     dom = "cross_gebv_fused"  # the one kernel on the step's critical path
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": bk[dom]}
-    prof = ROOT / "profiles" / "traffic.json"  # dram bytes per launch from the committed ncu capture
-    if prof.exists():
-        try:
-            roofline["traffic"] = json.loads(prof.read_text()).get(dom)
-        except Exception:
-            pass
+                "frac": kernels[dom]["achieved_gbs"] / peak,
+                "traffic": traffic_for(dom, f"E{E}_n{N_IND}_m{N_MARKERS}"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": bk[dom],
+                "whole_step_frac": alg[dom] / (t_value / K) / 1e9 / peak}
 
     # ---------------- e2e: public API, host actions in, GEBV + rewards out ----------------
-    del envs
+    del envs, env, sim, pop_words
     if args.skip_e2e:
         if rank == 0:
-            print(json.dumps({"value": total_envs * K / t_value, "ms_per_step": 1e3 * t_value / K, "replicas": REPLICAS,
-                              "kernels_ms": bk}), flush=True)
+            print(json.dumps({"value": total_envs * K / t_value, "ms_per_step": 1e3 * t_value / K, "replicas": replicas,
+                              "host_us_per_step": 1e6 * t_host / K, "kernels_ms": bk}), flush=True)
         return 0
-    envs_h = [make_env("host") for _ in range(REPLICAS)]
+    make_env = env_factory(total_envs)
+    envs_h = [make_env("host") for _ in range(replicas)]
 
     def host_step(i):
-        obs, rews, ter, tru, infos = envs_h[i % REPLICAS].step(acts_host[i % n_act])
-        if world > 1 and bool(tru[0]):
-            allgather_rewards(torch.from_numpy(np.ascontiguousarray(rews, dtype=np.float32)).to(dev), counts)
+        envs_h[i % replicas].step(acts_host[i % 16])
 
-    spin_up()
-    for i in range(max(W, REPLICAS)):
+    h.spin_up()
+    for i in range(max(W, replicas * (NUM_GENERATIONS + 1))):
         host_step(i)
-    timed(host_step, min(K, 500))  # untimed rehearsal, as above
+    h.timed(host_step, min(K, 500))  # untimed rehearsal, as above
     # timed in blocks (same total K): a block far slower than the others points at the box (clock state, a descheduled
     # host thread), not at the path; reported beside the total
     nblk = 4 if K >= 400 else 1
@@ -425,20 +497,50 @@ def run_ours(args):
     base = 0
     for b in range(nblk):
         kb = K // nblk + (1 if b < K % nblk else 0)
-        blocks.append(timed(lambda i, base=base: host_step(base + i), kb) / kb)
+        blocks.append(h.timed(lambda i, base=base: host_step(base + i), kb)[0] / kb)
         base += kb
     clocks_e2e = sampler_e2e.stop()
-    t_e2e = max_over_ranks(sum(bt * (K // nblk + (1 if b < K % nblk else 0)) for b, bt in enumerate(blocks)))
+    t_e2e = h.max_over_ranks(sum(bt * (K // nblk + (1 if b < K % nblk else 0)) for b, bt in enumerate(blocks)))
     h2d = count * N_IND * 2 * 4
     d2h = count * N_IND * 4 + (count * 4) / NUM_GENERATIONS
+    del envs_h
+
+    # ---------------- BASELINE config[4]: 512 envs per GPU (weak) and 4096 envs in total (strong) ----------------
+    c5 = None
+    if not args.no_c5:
+        c5 = {}
+        k5 = min(K, 40)
+        for name, tot in (("weak_512_per_gpu", 512 * world), ("strong_4096_total", 4096)):
+            b5, cnt5 = shard_range(tot, world, rank)
+            _, a5 = actions(cnt5, 4, 100 + rank)
+            reps5 = 1 if 2 * cnt5 * N_IND * 2560 > (126 << 20) else 2  # one population pair already exceeds L2
+            envs5, t5, th5, _ = vec_value_leg(h, env_factory(tot), a5, k5, 3, reps5)
+            del envs5, a5
+            torch.cuda.empty_cache()
+            c5[name] = {"workload": f"C5 vector env: {tot} envs over {world} GPU(s) ({cnt5} per GPU) x {N_IND} x {N_MARKERS}, "
+                                    f"NCCL reward all-gather" + (" (ncclAllGather through bg_allgather_f32)" if world > 1 else " (single GPU: no collective)"),
+                        "envs_total": tot, "envs_per_gpu": cnt5, "n_gpus": world, "steps": k5,
+                        "value": tot * k5 / t5, "unit": UNIT, "ms_per_step": 1e3 * t5 / k5, "host_us_per_step": 1e6 * th5 / k5,
+                        "scaling": "weak" if name.startswith("weak") else "strong",
+                        "frac_of_hbm_peak_whole_step": B_ALG_CROSS * cnt5 * N_IND * N_MARKERS / (t5 / k5) / 1e9 / peak}
+
+    # ---------------- the other named shapes (N = 1 only) ----------------
+    configs = None
+    if world == 1 and not args.no_legs:
+        from bench_legs import run_legs  # C1 / C3 / C4: scripts-level detail kept out of this file
+
+        configs = run_legs(h, torch, lib, local_rank, peak, measured_peaks()[0], int32_peak(), cpu=not args.no_cpu_baseline)
 
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_steps(2, 1, envs=ENVS_PER_GPU, min_seconds=10.0)
+        redraw = cpu_steps(1, 0, envs=8, shared_masks=False)
         cpu = {"value": res["env_steps_per_sec"], "unit": UNIT, "cores": res["cores"], "kind": "port",
                "sample": f"{res['steps']} full steps of {res['envs']} envs x {N_IND} x {N_MARKERS} "
-                         f"(cross + GEBV + reward) in {res['seconds']:.1f} s, C oracle with OpenMP"}
+                         f"(cross + GEBV + reward) in {res['seconds']:.1f} s, C oracle with OpenMP, shared-mask port "
+                         f"(2n masks drawn once per step, as the reference's vmap does)",
+               "per_env_redraw_value": redraw["env_steps_per_sec"], "note": CPU_NOTE}
 
     if rank == 0:
         value = total_envs * K / t_value
@@ -446,16 +548,21 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * t_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 bit planes (cross) + int64 fixed point (GEBV)", "data": "synthetic",
-            "config": config_dict(world, REPLICAS),
+            "config": config_dict(world, replicas),
             "offspring_markers_per_sec": value * N_IND * N_MARKERS,
+            "host_us_per_step": 1e6 * t_host / K,
             "clocks": clocks,
             "e2e": {"value": total_envs * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "VecBreedGym.step(numpy actions) -> numpy GEBV / rewards, one sync per step",
                     "us_per_step_by_block": [round(1e6 * bt, 1) for bt in blocks], "clocks": clocks_e2e},
             "gpu_launches": int(launches),
+            "gpu_launches_note": f"our kernels in {K} steps (counted over a repeat of the timed loop; "
+                                 f"{int(launches_total)} over warm-up + rehearsal + timed)",
             "roofline": roofline,
             "kernels": kernels,
             "cpu_baseline": cpu,
+            "c5": c5,
+            "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -482,12 +589,15 @@ def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 (512 envs/GPU, 4096 envs total) records")
+    ap.add_argument("--no-legs", action="store_true", help="skip the C1 / C3 / C4 legs")
     ap.add_argument("--replicas", type=int, default=REPLICAS, help="independent workload copies stepped round-robin")
     ap.add_argument("--skip-e2e", action="store_true", help="diagnostics: only the device-resident value")
+    ap.add_argument("--stream-priority", type=int, default=None, help="diagnostics: run on a torch stream of this priority")
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU,
                     help="envs per GPU (default 64 = BASELINE config C2; 512 = one GPU's share of C5, 4096 envs on 8 GPUs)")
     args = ap.parse_args()

@@ -48,13 +48,19 @@ _SIGNATURES = {
     "bg_meiosis_masks": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "bg_gebv": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "bg_gebv_algo": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    "bg_gebv_digits": (c_int, [c_void_p]),
     "bg_reduce_max": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "bg_reduce_mean": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "bg_reset_indices": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "bg_vec_reset": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
-    "bg_vec_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+    "bg_vec_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bg_engine_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
+    "bg_comm_unique_id": (c_int, [c_void_p]),
+    "bg_comm_create": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "bg_comm_destroy": (c_int, [c_void_p]),
+    "bg_allgather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 _lib = None

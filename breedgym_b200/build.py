@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libbreedgym_b200.so"
 OBJ_DIR = PKG / "_obj"
-SOURCES = ["api.cu", "meiosis.cu", "gebv.cu", "gebv_tc.cu", "gebv_tc2.cu", "cross_gebv.cu", "layout.cu"]
+SOURCES = ["api.cu", "meiosis.cu", "gebv.cu", "gebv_tc2.cu", "cross_gebv.cu", "layout.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         print("\n".join(log))
     link = [nvcc, "-shared", "-o", str(OUT), *[str(o) for _, o, _ in results],
-            "-gencode", "arch=compute_100a,code=sm_100a"]
+            "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -176,7 +176,54 @@ int bg_engine_create(int device, bg_engine **out)
     e->device = device;
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    // tuning switches: the environment is read HERE, once (BG_OPT_<NAME>); nothing on the step path calls getenv
+    static const char *const names[] = {"fuse", "gebv_algo", "lookahead", "mask_nt", "mask_big_ctas", "blend_env_chunk",
+                                        "copy_engine", "mapped_d2h_max", "tc_target_ctas", "timing", "gebv_digits"};
+    for (const char *name : names) {
+        std::string env = "BG_OPT_";
+        for (const char *c = name; *c; ++c) env += (char)toupper(*c);
+        if (const char *v = getenv(env.c_str())) {
+            if (bg_engine_set_option(e, name, atoll(v)) != BG_OK) {
+                delete e;
+                return BG_EINVAL;
+            }
+        }
+    }
     *out = e;
+    return BG_OK;
+}
+
+int bg_engine_set_option(bg_engine *eng, const char *name, int64_t value)
+{
+    BG_REQUIRE(eng && name, BG_EINVAL, "bg_engine_set_option: null argument");
+    bg_options &o = eng->opt;
+    const std::string n(name);
+    if (n == "fuse") o.fuse = value != 0;
+    else if (n == "gebv_algo") {
+        BG_REQUIRE(value >= 0 && value <= 3, BG_EINVAL, "gebv_algo must be 0..3");
+        o.gebv_algo = (int)value;
+    } else if (n == "lookahead") {
+        BG_REQUIRE(value >= 0, BG_EINVAL, "lookahead must be >= 0");
+        o.lookahead = (int)(value > BG_BATCH_MAX ? BG_BATCH_MAX : value);
+    } else if (n == "mask_nt") {
+        BG_REQUIRE(value >= 32 && value <= 256, BG_EINVAL, "mask_nt must be 32..256");
+        o.mask_nt = (int)value / 32 * 32;
+    } else if (n == "mask_big_ctas") o.mask_big_ctas = value != 0;
+    else if (n == "blend_env_chunk") {
+        BG_REQUIRE(value >= 1, BG_EINVAL, "blend_env_chunk must be >= 1");
+        o.blend_env_chunk = (int)value;
+    } else if (n == "copy_engine") o.copy_engine = value != 0;
+    else if (n == "mapped_d2h_max") o.mapped_d2h_max = value;
+    else if (n == "tc_target_ctas") o.tc_target_ctas = value;
+    else if (n == "timing") o.timing = value != 0;
+    else if (n == "gebv_digits") {
+        BG_REQUIRE(value == 0 || (value >= 4 && value <= 8), BG_EINVAL, "gebv_digits must be 0 (auto) or 4..8");
+        BG_REQUIRE(eng->m == 0, BG_ESTATE, "gebv_digits must be set before bg_engine_set_map");
+        o.gebv_digits = (int)value;
+    } else {
+        bg_set_error("unknown option '" + n + "'");
+        return BG_EINVAL;
+    }
     return BG_OK;
 }
 
@@ -202,12 +249,13 @@ int bg_engine_destroy(bg_engine *eng)
             cudaStreamSynchronize(eng->side);
             cudaStreamDestroy(eng->side);
         }
-        for (auto &sl : eng->slots) {
-            cudaFree(sl.mask);
-            cudaFree(sl.mut);
-            if (sl.ready) cudaEventDestroy(sl.ready);
-            if (sl.freed) cudaEventDestroy(sl.freed);
+        for (auto &b : eng->batches) {
+            cudaFree(b.mask);
+            cudaFree(b.mut);
+            if (b.ready) cudaEventDestroy(b.ready);
+            if (b.freed) cudaEventDestroy(b.freed);
         }
+        if (eng->tmp_event) cudaEventDestroy(eng->tmp_event);
         cudaFree(eng->d_mut);
         cudaFree(eng->d_acc);
         for (int i = 0; i < 2; ++i) {
@@ -226,7 +274,7 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
     BG_REQUIRE(n_traits >= 0 && (n_traits == 0 || effects), BG_EINVAL, "bad marker effects");
     free_map(eng);
     if (eng->side) BG_CUDA(cudaStreamSynchronize(eng->side));
-    for (auto &sl : eng->slots) sl.valid = false;  // masks depend on the thresholds
+    for (auto &b : eng->batches) b.valid = false;  // masks depend on the thresholds
     eng->m = n_markers;
     eng->W = (int32_t)((n_markers + 31) / 32);
     eng->Wpad = (int32_t)bg_words_per_row(n_markers);
@@ -240,24 +288,55 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
     BG_CUDA(cudaMemcpy(eng->d_thr, thr.data(), nthr * sizeof(uint32_t), cudaMemcpyHostToDevice));
 
     if (n_traits > 0) {
-        // fixed point: w_fix = rint(w * 2^s), s = largest shift with 2*sum|w| * 2^s < 2^54, so that any GEBV sum, rounding of
-        // the w_fix included (+ at most one unit per marker), stays below 2^55 in magnitude (the tensor-core kernels
-        // sum 64x these integers, see the digit table below, and must stay inside int64)
+        // Fixed point: w_fix = rint(w * 2^s), one scale s per trait.  Sums of w_fix are exact integers, so a GEBV does
+        // not depend on the summation order and is rounded once, to float32.  The tensor-core kernels feed w_fix as D
+        // balanced base-256 int8 digits per effect; D (and with it s) is chosen PER MAP:
+        //   * worst-case quantisation error of a GEBV: m * 2^-s (dosage <= 2, |w - w_fix 2^-s| <= 2^-(s+1)); required
+        //     <= 2^-25 * sum|w|, i.e. a quarter of float32's epsilon relative to the GEBV's range 2 sum|w| -- the
+        //     reference's own float32 dot (TraitModel.__call__) carries 2^-24 * sum|w d| in the worst case;
+        //   * D = the digits that takes (>= 4), raised to the most that costs nothing (the GEMM's N = D * T is padded
+        //     to a multiple of 16: one trait always gets all 8); option gebv_digits fixes it instead;
+        //   * s = the largest scale D digits hold (64 |w_fix| <= 2^(8D-2): the prescaled operand, below) that keeps any
+        //     sum, rounding included, below 2^55 (K-split accumulators: 56-bit sums + an 8-bit arrival count).
         const size_t stride = (size_t)((eng->Wpad + 7) / 8) * 256;
         std::vector<long long> wfix(stride * n_traits, 0ll);
         std::vector<double> inv(n_traits, 1.0);
+        std::vector<double> sums(n_traits, 0.0), maxs(n_traits, 0.0);
+        int need_bits = 0;  // max over traits of: bits of the largest |w_fix| at the minimum scale
         for (int t = 0; t < n_traits; ++t) {
-            double sum = 0.0;
+            double sum = 0.0, mx = 0.0;
             for (int64_t j = 0; j < n_markers; ++j) {
                 const double w = (double)effects[j * n_traits + t];
                 BG_REQUIRE(isfinite(w), BG_EINVAL, "marker effects must be finite");
                 sum += fabs(w);
+                if (fabs(w) > mx) mx = fabs(w);
             }
-            int s = 0;
+            sums[t] = sum;
+            maxs[t] = mx;
             if (sum > 0.0) {
-                int ex;
-                frexp(2.0 * sum, &ex);  // 2*sum < 2^ex
-                s = 54 - ex;
+                int e_mean, e_max;
+                frexp(sum / (double)n_markers, &e_mean);  // mean|w| >= 2^(e_mean-1)
+                frexp(mx, &e_max);                        // max|w| < 2^e_max
+                const int s_min = 25 - (e_mean - 1);      // 2^-s <= 2^-25 * mean|w|
+                const int bits = s_min + e_max;           // |w_fix| < 2^bits at s_min
+                if (bits > need_bits) need_bits = bits;
+            }
+        }
+        int D = eng->opt.gebv_digits;
+        if (D == 0) {
+            D = (need_bits + 8 + 7) / 8;  // |w_fix| <= 2^(8D-8)  <=>  bits <= 8D - 8
+            if (D < 4) D = 4;
+            if (D > 8) D = 8;
+            while (D < 8 && ((D + 1) * n_traits + 15) / 16 == (D * n_traits + 15) / 16) ++D;  // digits that cost nothing
+        }
+        for (int t = 0; t < n_traits; ++t) {
+            int s = 0;
+            if (sums[t] > 0.0) {
+                int ex_sum, ex_max;
+                frexp(2.0 * sums[t], &ex_sum);  // 2*sum < 2^ex_sum
+                frexp(maxs[t], &ex_max);
+                s = 54 - ex_sum;                                       // any sum stays below 2^55
+                if (s > 8 * D - 8 - ex_max) s = 8 * D - 8 - ex_max;    // |w_fix| <= 2^(8D-8): 64x it fits D balanced digits
                 if (s > 1000) s = 1000;
                 if (s < -1000) s = -1000;
             }
@@ -270,17 +349,18 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
         BG_CUDA(cudaMalloc(&eng->d_inv_scale, n_traits * sizeof(double)));
         BG_CUDA(cudaMemcpy(eng->d_inv_scale, inv.data(), n_traits * sizeof(double), cudaMemcpyHostToDevice));
 
-        // tensor-core digit table: w_fix = sum_d digit_d * 256^d with balanced digits in [-128,127],
-        // stored per 128-marker step as [N/8][8][8 rows][16 B] core matrices (gebv_tc*.cu).  Inside
-        // a 32-marker word, K index 4*s + b holds marker 8*b + s (matches the kernels' expansion).
-        // PRESCALED operand: the kernels feed the dosage of marker 8*b + s as the unsigned byte
+        // tensor-core digit table: w_fix = sum_d digit_d * 256^d with balanced digits in [-128,127], D digits per
+        // effect (column D*t + d), stored per 128-marker step as [N/8][8][8 rows][16 B] core matrices
+        // (gebv_tc2.cu, cross_gebv.cu).  Inside a 32-marker word, K index 4*s + b holds marker 8*b + s (matches the
+        // kernels' expansion).  PRESCALED operand: the kernels feed the dosage of marker 8*b + s as the unsigned byte
         // dosage * 4^(s/2) (a masked 2-bit field left where it sits in its byte: one LOP3, no shift),
         // so the digits here are those of w_fix * 4^(3 - s/2) and every tensor-core sum is exactly
         // 64x the plain fixed-point sum (shifted back in the kernels' epilogues).
         eng->tc_N = 0;
+        eng->tc_D = D;
         eng->tc_steps = 0;
-        if (n_traits <= bg_gebv_tc_max_traits()) {
-            const int N = ((8 * n_traits + 15) / 16) * 16;
+        if (D * n_traits <= 256) {
+            const int N = ((D * n_traits + 15) / 16) * 16;
             const int64_t steps = eng->Wpad / 4;
             std::vector<signed char> dig((size_t)(steps + 1) * N * 128, 0);  // one zero step of slack
             for (int t = 0; t < n_traits; ++t)
@@ -291,13 +371,14 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
                     const int word = (int)(j % 128) / 32, bit = (int)(j % 32);
                     w *= 1ll << (2 * (3 - (bit % 8) / 2));
                     const int k = word * 32 + 4 * (bit % 8) + bit / 8;
-                    for (int d = 0; d < 8; ++d) {
+                    for (int d = 0; d < D; ++d) {
                         const int dgt = (int)(((w + 128) & 255) - 128);
                         w = (w - dgt) >> 8;
-                        const int n = 8 * t + d;
+                        const int n = D * t + d;
                         const size_t off = (((size_t)st * (N / 8) + n / 8) * 8 + k / 16) * 128 + (n % 8) * 16 + k % 16;
                         dig[off] = (signed char)dgt;
                     }
+                    BG_REQUIRE(w == 0, BG_ESTATE, "internal: a fixed-point effect does not fit its digits");
                 }
             BG_CUDA(cudaMalloc(&eng->d_wdig, dig.size()));
             BG_CUDA(cudaMemcpy(eng->d_wdig, dig.data(), dig.size(), cudaMemcpyHostToDevice));
@@ -307,6 +388,8 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
     }
     return BG_OK;
 }
+
+int bg_gebv_digits(bg_engine *eng) { return eng ? eng->tc_D : 0; }
 
 int bg_pack(bg_engine *eng, const uint8_t *bool_in, uint32_t *packed_out, int64_t rows, void *stream)
 {
@@ -334,137 +417,190 @@ int bg_gather_individuals(bg_engine *eng, const uint32_t *src, const int32_t *id
     return bg_launch_gather(src, idx, dst, E, n_src, n, src_env_rows, eng->Wpad, (cudaStream_t)stream);
 }
 
-// ---- crossover-mask slots (vector env) ------------------------------------------------------
-static bool slot_matches(const bg_mask_slot &sl, const uint32_t key[2], int layout, int schedule, int64_t rows)
+// ---- crossover-mask batches (vector env) -----------------------------------------------------
+// key chain of chromax's Simulator.cross: `random_key, k = split(random_key)`
+static inline void chain_next(uint32_t state[2], int layout, uint32_t k[2])
 {
-    // timing experiments only (results are wrong): any generated slot serves any key -> no mask kernel in the step
-    static const bool reuse = getenv("BG_DEBUG_REUSE_MASKS") != nullptr;
-    if (reuse && sl.valid && sl.rows == rows) return true;
-    return sl.valid && sl.key[0] == key[0] && sl.key[1] == key[1] && sl.layout == layout && sl.schedule == schedule &&
-           sl.rows == rows;
+    const TfKey cur = tf_make_key(state[0], state[1]);
+    const TfKey after = tf_split_at(cur, 0, 2, layout), kk = tf_split_at(cur, 1, 2, layout);
+    state[0] = after.k0;
+    state[1] = after.k1;
+    k[0] = kk.k0;
+    k[1] = kk.k1;
 }
 
-static int slot_prepare(bg_engine *eng, bg_mask_slot &sl, int64_t rows)
+// how many keys' masks one batch buffer may hold (64 MB per buffer at most; 1 for giant maps)
+static int batch_capacity(const bg_engine *eng, int64_t rows)
 {
-    const size_t words = (size_t)rows * eng->Wpad;
-    int rc = bg_reserve_u32(&sl.mask, &sl.cap, words);
-    if (rc) return rc;
-    if (eng->mut_thr) {
-        rc = bg_reserve_u32(&sl.mut, &sl.mut_cap, words);
-        if (rc) return rc;
+    const size_t per_key = (size_t)rows * eng->Wpad * sizeof(uint32_t) * (eng->mut_thr ? 2 : 1);
+    size_t c = per_key ? (size_t(64) << 20) / per_key : BG_BATCH_MAX;
+    if (c > (size_t)BG_BATCH_MAX) c = BG_BATCH_MAX;
+    return c < 1 ? 1 : (int)c;
+}
+
+static bool batch_lookup(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, int *bi, int *pos)
+{
+    for (int i = 0; i < BG_MASK_BATCHES; ++i) {
+        const bg_mask_batch &b = eng->batches[i];
+        if (!b.valid || b.layout != layout || b.schedule != schedule || b.rows != rows) continue;
+        for (int p = 0; p < b.count; ++p)
+            if (b.keys[p][0] == key[0] && b.keys[p][1] == key[1]) {
+                *bi = i;
+                *pos = p;
+                return true;
+            }
     }
-    if (!sl.ready) BG_CUDA(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
-    if (!sl.freed) BG_CUDA(cudaEventCreateWithFlags(&sl.freed, cudaEventDisableTiming));
-    return BG_OK;
+    return false;
 }
 
-static int slot_generate(bg_engine *eng, bg_mask_slot &sl, const uint32_t key[2], int layout, int schedule, int64_t rows,
-                         cudaStream_t on, int small_ctas = 0)
+// generate the masks of keys[0..count) into batch `bi` on stream `on` (after the buffer's readers are done)
+static int batch_generate(bg_engine *eng, int bi, int count, const uint32_t (*keys)[2], const uint32_t *state_after, int layout,
+                          int schedule, int64_t rows, cudaStream_t on, int small_ctas)
 {
-    sl.valid = false;
-    int rc = slot_prepare(eng, sl, rows);
-    if (rc) return rc;
-    rc = bg_launch_meiosis_rows(eng, BG_ROWS_MASK, rows, key, layout, schedule, sl.mask, eng->mut_thr ? sl.mut : nullptr, nullptr,
-                                nullptr, 0, 0, nullptr, on, small_ctas);
-    if (rc) return rc;
-    BG_CUDA(cudaEventRecord(sl.ready, on));
-    sl.ready_set = true;
-    sl.valid = true;
-    sl.key[0] = key[0];
-    sl.key[1] = key[1];
-    sl.layout = layout;
-    sl.schedule = schedule;
-    sl.rows = rows;
-    return BG_OK;
-}
-
-// masks for `key`, usable by work enqueued on `st` after this returns
-static int masks_acquire(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, cudaStream_t st, int *slot)
-{
-    for (int i = 0; i < BG_MASK_SLOTS; ++i)
-        if (slot_matches(eng->slots[i], key, layout, schedule, rows)) {
-            BG_CUDA(cudaStreamWaitEvent(st, eng->slots[i].ready, 0));  // generated ahead of time (or earlier on st)
-            *slot = i;
-            return BG_OK;
+    bg_mask_batch &b = eng->batches[bi];
+    b.valid = false;
+    if (!b.ready) BG_CUDA(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
+    if (!b.freed) BG_CUDA(cudaEventCreateWithFlags(&b.freed, cudaEventDisableTiming));
+    if (!eng->tmp_event) BG_CUDA(cudaEventCreateWithFlags(&eng->tmp_event, cudaEventDisableTiming));
+    // readers of the old contents: everything enqueued so far on the stream that used it
+    if (b.used && b.use_stream != on) {
+        BG_CUDA(cudaEventRecord(eng->tmp_event, b.use_stream));
+        BG_CUDA(cudaStreamWaitEvent(on, eng->tmp_event, 0));
+    }
+    if (b.freed_set) BG_CUDA(cudaStreamWaitEvent(on, b.freed, 0));
+    if (b.gen_stream && b.gen_stream != on) BG_CUDA(cudaStreamWaitEvent(on, b.ready, 0));  // a stale generation may still be writing
+    b.used = false;
+    b.freed_set = false;
+    b.use_stream = nullptr;
+    const size_t words = (size_t)count * rows * eng->Wpad;
+    if (b.cap < words || (eng->mut_thr && b.mut_cap < words)) {
+        // growing the buffer frees the old one: cudaFree synchronises the device, so nothing can still be reading it
+        const size_t want = (size_t)batch_capacity(eng, rows) * rows * eng->Wpad;
+        int rc = bg_reserve_u32(&b.mask, &b.cap, want > words ? want : words);
+        if (rc) return rc;
+        if (eng->mut_thr) {
+            rc = bg_reserve_u32(&b.mut, &b.mut_cap, want > words ? want : words);
+            if (rc) return rc;
         }
-    const int i = (eng->last_slot + 1) % BG_MASK_SLOTS;
-    bg_mask_slot &sl = eng->slots[i];
-    if (sl.ready_set) BG_CUDA(cudaStreamWaitEvent(st, sl.ready, 0));  // a stale lookahead may still be writing the slot
-    if (sl.freed_set) BG_CUDA(cudaStreamWaitEvent(st, sl.freed, 0));
-    const int rc = slot_generate(eng, sl, key, layout, schedule, rows, st);
+    }
+    int rc = bg_launch_mask_batch(eng, rows, count, keys, layout, schedule, b.mask, eng->mut_thr ? b.mut : nullptr, on, small_ctas);
     if (rc) return rc;
-    *slot = i;
+    BG_CUDA(cudaEventRecord(b.ready, on));
+    b.gen_stream = on;
+    b.synced_stream = on;  // work enqueued on `on` later is ordered behind the kernel anyway
+    b.count = count;
+    for (int p = 0; p < count; ++p) {
+        b.keys[p][0] = keys[p][0];
+        b.keys[p][1] = keys[p][1];
+    }
+    b.has_state = state_after != nullptr;
+    if (state_after) {
+        b.state_after[0] = state_after[0];
+        b.state_after[1] = state_after[1];
+    }
+    b.layout = layout;
+    b.schedule = schedule;
+    b.rows = rows;
+    b.valid = true;
+    b.stamp = ++eng->use_clock;
     return BG_OK;
 }
 
-static int masks_release(bg_engine *eng, int slot, cudaStream_t st)
+// least recently used batch buffer other than `keep`
+static int batch_victim(const bg_engine *eng, int keep)
 {
-    bg_mask_slot &sl = eng->slots[slot];
-    BG_CUDA(cudaEventRecord(sl.freed, st));
-    sl.freed_set = true;
-    eng->last_slot = slot;
-    return BG_OK;
-}
-
-// start generating the masks of an UPCOMING cross key on the side stream, in a slot that holds neither the current
-// masks (`cur`) nor those of another upcoming key (`keep`, -1: none); returns the slot used (or already holding them)
-// `after_step`: start only once the kernels of the current step are done (their `freed` record).  The host-facing
-// step synchronises and leaves the GPU idle while the host works: the integer-bound mask kernel then runs in that gap
-// instead of competing with the step kernel for issue slots.  The device-resident pipeline has no gap: there the mask
-// kernels run TWO steps ahead, so that they only fill the slots the step kernels leave free and never delay their start.
-static int masks_lookahead(bg_engine *eng, const uint32_t key[2], int layout, int schedule, int64_t rows, int cur, int keep,
-                           bool after_step, int *used)
-{
-    for (int i = 0; i < BG_MASK_SLOTS; ++i)
-        if (slot_matches(eng->slots[i], key, layout, schedule, rows)) {
-            *used = i;
-            return BG_OK;
-        }
-    if (!eng->side) BG_CUDA(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
     int v = -1;
-    for (int i = 0; i < BG_MASK_SLOTS; ++i)
-        if (i != cur && i != keep) v = i;
-    bg_mask_slot &sl = eng->slots[v];
-    if (after_step && eng->slots[cur].freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, eng->slots[cur].freed, 0));
-    if (sl.freed_set) BG_CUDA(cudaStreamWaitEvent(eng->side, sl.freed, 0));  // its last reader (an earlier step) is done
-    *used = v;
-    // overlapping the step kernel: small CTAs that fit beside its two CTAs per SM
-    static const bool big = getenv("BG_MASK_BIG_CTAS") != nullptr;  // diagnostics
-    return slot_generate(eng, sl, key, layout, schedule, rows, eng->side, (after_step || big) ? 0 : 1);
+    for (int i = 0; i < BG_MASK_BATCHES; ++i) {
+        if (i == keep) continue;
+        if (!eng->batches[i].valid) return i;
+        if (v < 0 || eng->batches[i].stamp < eng->batches[v].stamp) v = i;
+    }
+    return v;
+}
+
+// Masks of `key` for work enqueued on `st` after this returns.  `state_after` (may be NULL): the key-chain state
+// after `key` was drawn; when given, the batch that CONTINUES the chain is generated on the side stream as soon as the
+// first key of a batch is used, doubling in length up to the lookahead option (1, 2, 4, 8, 8, ...), so that a steady
+// stream of steps never waits for masks and a short run does not pay for masks it never uses.
+static int masks_acquire(bg_engine *eng, const uint32_t key[2], const uint32_t *state_after, int layout, int schedule, int64_t rows,
+                         cudaStream_t st, const uint32_t **mask, const uint32_t **mut, int *batch, bool *first)
+{
+    int bi = -1, pos = 0;
+    if (!batch_lookup(eng, key, layout, schedule, rows, &bi, &pos)) {
+        bi = batch_victim(eng, -1);
+        const uint32_t keys[1][2] = {{key[0], key[1]}};
+        const int rc = batch_generate(eng, bi, 1, keys, state_after, layout, schedule, rows, st, 0);
+        if (rc) return rc;
+        pos = 0;
+    }
+    bg_mask_batch &b = eng->batches[bi];
+    if (b.synced_stream != st) {
+        BG_CUDA(cudaStreamWaitEvent(st, b.ready, 0));
+        b.synced_stream = st;
+    }
+    if (b.used && b.use_stream != st) {  // readers move to another stream: leave a marker behind the old ones
+        BG_CUDA(cudaEventRecord(b.freed, b.use_stream));
+        b.freed_set = true;
+    }
+    b.used = true;
+    b.use_stream = st;
+    b.stamp = ++eng->use_clock;
+    const size_t off = (size_t)pos * rows * eng->Wpad;
+    *mask = b.mask + off;
+    *mut = eng->mut_thr ? b.mut + off : nullptr;
+
+    *batch = bi;
+    *first = pos == 0;
+    return BG_OK;
+}
+
+// lookahead: called after the step that used the FIRST key of chain batch `bi` has been enqueued -- make sure the batch
+// that continues the chain exists or is being generated (on the side stream, behind nothing: the mask kernel's small
+// CTAs run beside the step kernel)
+static int masks_continue(bg_engine *eng, int bi, cudaStream_t st)
+{
+    const bg_mask_batch &b = eng->batches[bi];
+    if (!b.has_state || eng->opt.lookahead <= 0) return BG_OK;
+    const int layout = b.layout, schedule = b.schedule;
+    const int64_t rows = b.rows;
+    uint32_t state[2] = {b.state_after[0], b.state_after[1]};
+    uint32_t keys[BG_BATCH_MAX][2];
+    chain_next(state, layout, keys[0]);
+    int ci, cp;
+    if (batch_lookup(eng, keys[0], layout, schedule, rows, &ci, &cp)) return BG_OK;
+    int count = 2 * b.count;
+    const int cap = batch_capacity(eng, rows);
+    if (count > eng->opt.lookahead) count = eng->opt.lookahead;
+    if (count > cap) count = cap;
+    for (int p = 1; p < count; ++p) chain_next(state, layout, keys[p]);
+    if (!eng->side) BG_CUDA(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
+    (void)st;
+    // small CTAs that fit beside the step kernel's two CTAs per SM (cross_gebv.cu)
+    return batch_generate(eng, batch_victim(eng, bi), count, keys, state, layout, schedule, rows, eng->side,
+                          eng->opt.mask_big_ctas ? 0 : 1);
 }
 
 // gebv_out != nullptr: also score the offspring; fused into one kernel when the tensor-core path applies
 static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *parents, uint32_t *out, int64_t E, int64_t n_src,
-                           int64_t n, const uint32_t cross_key[2], const uint32_t *next_key, int layout, int schedule,
-                           float *gebv_out, cudaStream_t st, bool lookahead_after_step = false)
+                           int64_t n, const uint32_t cross_key[2], const uint32_t *state_after, int layout, int schedule,
+                           float *gebv_out, cudaStream_t st)
 {
-    // One fused cross+GEBV kernel (cross_gebv.cu: 47 us at C2 against 33 + 32 us for blend + GEBV) whenever the
-    // tensor-core path applies; BG_NO_FUSE=1 selects the two-kernel path (cross-checks, tuning).
-    const bool no_fuse = getenv("BG_NO_FUSE") != nullptr;
-    int slot = 0;
-    int rc = masks_acquire(eng, cross_key, layout, schedule, 2 * n, st, &slot);
+    const uint32_t *mask = nullptr, *mut = nullptr;
+    int batch = -1;
+    bool first = false;
+    int rc = masks_acquire(eng, cross_key, state_after, layout, schedule, 2 * n, st, &mask, &mut, &batch, &first);
     if (rc) return rc;
-    const bg_mask_slot &sl = eng->slots[slot];
-    if (gebv_out && !no_fuse && bg_cross_gebv_fused_ok(eng, E, n_src, n)) {
-        rc = bg_launch_cross_gebv_fused(eng, pop, parents, sl.mask, out, E, n_src, n, gebv_out, st);
+    // One fused cross+GEBV kernel (cross_gebv.cu) whenever the tensor-core path applies; option fuse=0 selects the
+    // two-kernel path (cross-checks, tuning).
+    if (gebv_out && eng->opt.fuse && bg_cross_gebv_fused_ok(eng, E, n_src, n)) {
+        rc = bg_launch_cross_gebv_fused(eng, pop, parents, mask, out, E, n_src, n, gebv_out, st);
     } else {
         // blend and GEBV are adjacent in the stream (no event between them) so that the GEBV kernel's
         // programmatic dependent launch can overlap its prologue with the blend's tail
-        rc = bg_launch_blend(eng, pop, parents, sl.mask, eng->mut_thr ? sl.mut : nullptr, out, E, n_src, n, st);
+        rc = bg_launch_blend(eng, pop, parents, mask, mut, out, E, n_src, n, st);
         if (!rc && gebv_out) rc = bg_launch_gebv(eng, out, E * n, gebv_out, 0, st);
     }
-    if (rc) return rc;
-    rc = masks_release(eng, slot, st);
-    if (rc) return rc;
-    static const bool no_lookahead = getenv("BG_NO_LOOKAHEAD") != nullptr;  // diagnostics
-    if (next_key && !no_lookahead) {
-        // next_key[0..1]: the next step's key, next_key[2..3]: the one after it
-        int s1 = -1, s2 = -1;
-        rc = masks_lookahead(eng, next_key, layout, schedule, 2 * n, slot, -1, lookahead_after_step, &s1);
-        static const bool one_ahead = getenv("BG_LOOKAHEAD1") != nullptr;  // diagnostics
-        if (!rc && !lookahead_after_step && !one_ahead)
-            rc = masks_lookahead(eng, next_key + 2, layout, schedule, 2 * n, slot, s1, false, &s2);
-    }
+    if (!rc && first) rc = masks_continue(eng, batch, st);
     return rc;
 }
 
@@ -599,12 +735,11 @@ int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, cons
 // Host <-> device transfers of the host-facing step.  SMALL ones (single-env actions / GEBVs, per-env rewards) go through
 // a copy kernel on the mapped pinned buffer when the host pointer is device-accessible (pinned + 16-byte aligned): no
 // copy-engine hand-off (C1 step 100.7 -> 92.8 us).  Larger ones use the copy engine: at the 189 KB + 95 KB of the 64-env
-// step the zero-copy kernels measured slower (105 vs 98 us per step).  BG_COPY_ENGINE=1: always the copy engine.
+// step the zero-copy kernels measured slower (105 vs 98 us per step).  Option copy_engine=1: always the copy engine.
 constexpr size_t BG_MAPPED_COPY_MAX = 32 * 1024;
-static void *mapped_device_pointer(const void *host)
+static void *mapped_device_pointer(const bg_engine *eng, const void *host)
 {
-    static const bool off = getenv("BG_COPY_ENGINE") != nullptr;
-    if (off || ((uintptr_t)host & 15)) return nullptr;
+    if (eng->opt.copy_engine || ((uintptr_t)host & 15)) return nullptr;
     void *dp = nullptr;
     if (cudaHostGetDevicePointer(&dp, const_cast<void *>(host), 0) != cudaSuccess) {
         cudaGetLastError();  // pageable memory: not an error for us
@@ -613,98 +748,99 @@ static void *mapped_device_pointer(const void *host)
     return dp;
 }
 
-static int copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st)
+static int copy_h2d(const bg_engine *eng, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st)
 {
-    if (void *dp = (bytes % 4 == 0 && bytes <= BG_MAPPED_COPY_MAX) ? mapped_device_pointer(src_host) : nullptr)
+    if (void *dp = (bytes % 4 == 0 && bytes <= BG_MAPPED_COPY_MAX) ? mapped_device_pointer(eng, src_host) : nullptr)
         return bg_launch_copy_mapped(dp, dst_dev, bytes, st);
     BG_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
     return BG_OK;
 }
 
-static int copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st)
+static int copy_d2h(const bg_engine *eng, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st)
 {
-    static const size_t d2h_max = getenv("BG_MAPPED_D2H_MAX") ? (size_t)atoll(getenv("BG_MAPPED_D2H_MAX")) : BG_MAPPED_COPY_MAX;  // tuning
-    if (void *dp = (bytes % 4 == 0 && bytes <= d2h_max) ? mapped_device_pointer(dst_host) : nullptr)
+    if (void *dp = (bytes % 4 == 0 && (long long)bytes <= eng->opt.mapped_d2h_max) ? mapped_device_pointer(eng, dst_host) : nullptr)
         return bg_launch_copy_mapped(src_dev, dp, bytes, st);
     BG_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
     return BG_OK;
 }
 
-// BG_TIMING=1: host-side wall time of each phase of bg_vec_step, printed every 1000 calls (diagnostics)
+// option timing=1: host-side wall time of each phase of bg_vec_step, printed every 1000 calls (diagnostics)
 struct StepTimer {
-    bool on;
-    double acc[6] = {0, 0, 0, 0, 0, 0};
+    double acc[4] = {0, 0, 0, 0};
     long calls = 0;
     std::chrono::steady_clock::time_point t;
-    StepTimer() : on(getenv("BG_TIMING") != nullptr) {}
-    void start()
+    void start(bool on)
     {
         if (on) t = std::chrono::steady_clock::now();
     }
-    void lap(int i)
+    void lap(bool on, int i)
     {
         if (!on) return;
         const auto n = std::chrono::steady_clock::now();
         acc[i] += std::chrono::duration<double, std::micro>(n - t).count();
         t = n;
     }
-    void done()
+    void done(bool on)
     {
         if (!on || ++calls % 1000) return;
-        fprintf(stderr, "[bg_vec_step us/call] h2d %.1f cross %.1f gebv %.1f reduce %.1f d2h %.1f sync %.1f\n", acc[0] / calls,
-                acc[1] / calls, acc[2] / calls, acc[3] / calls, acc[4] / calls, acc[5] / calls);
+        fprintf(stderr, "[bg_vec_step us/call] h2d %.2f step %.2f reduce+d2h %.2f sync %.2f\n", acc[0] / calls, acc[1] / calls,
+                acc[2] / calls, acc[3] / calls);
     }
 };
 static StepTimer g_step_timer;
 
 int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_t *actions_host, int32_t *actions_dev, int64_t E,
-                int64_t n_src, int64_t n, const uint32_t cross_key[2], const uint32_t *next_cross_key, int layout, int schedule,
-                float *gebv_dev, float *reward_dev, float *gebv_host, float *reward_host, void *stream)
+                int64_t n_src, int64_t n, uint32_t key_state[2], int layout, int schedule, float *gebv_dev, float *reward_dev,
+                float *gebv_host, float *reward_host, void *stream)
 {
     BG_ENTER(eng);
     BG_REQUIRE(actions_dev && gebv_dev, BG_EINVAL, "bg_vec_step: null device buffer");
     BG_REQUIRE(!reward_host || reward_dev, BG_EINVAL, "bg_vec_step: reward_host needs reward_dev");
-    BG_REQUIRE(E > 0 && n > 0 && n_src > 0 && cross_key && pop && out, BG_EINVAL, "bg_vec_step: bad argument");
+    BG_REQUIRE(E > 0 && n > 0 && n_src > 0 && key_state && pop && out, BG_EINVAL, "bg_vec_step: bad argument");
+    BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool tm_on = eng->opt.timing != 0;
     StepTimer &tm = g_step_timer;
-    tm.start();
+    tm.start(tm_on);
     int rc;
     if (actions_host) {
-        rc = copy_h2d(actions_dev, actions_host, (size_t)E * n * 2 * sizeof(int32_t), st);
+        rc = copy_h2d(eng, actions_dev, actions_host, (size_t)E * n * 2 * sizeof(int32_t), st);
         if (rc) return rc;
     }
-    tm.lap(0);
+    tm.lap(tm_on, 0);
+    // random_key, k = split(random_key)   (chromax Simulator.cross)
+    uint32_t state[2] = {key_state[0], key_state[1]}, k[2];
+    chain_next(state, layout, k);
     if (E == 1) {
-        rc = bg_launch_meiosis_rows(eng, BG_ROWS_CROSS, 2 * n, cross_key, layout, schedule, nullptr, nullptr, pop, actions_dev,
-                                    n_src, 0, out, st);
+        rc = bg_launch_meiosis_rows(eng, BG_ROWS_CROSS, 2 * n, k, layout, schedule, nullptr, nullptr, pop, actions_dev, n_src, 0, out,
+                                    st);
         if (!rc) rc = bg_launch_gebv(eng, out, n, gebv_dev, 0, st);
     } else {
-        rc = cross_envs_impl(eng, pop, actions_dev, out, E, n_src, n, cross_key, next_cross_key, layout, schedule, gebv_dev, st,
-                             gebv_host != nullptr || reward_host != nullptr);
+        rc = cross_envs_impl(eng, pop, actions_dev, out, E, n_src, n, k, state, layout, schedule, gebv_dev, st);
     }
     if (rc) return rc;
-    tm.lap(1);
-    tm.lap(2);
+    key_state[0] = state[0];  // the chain advances only when the step has been enqueued
+    key_state[1] = state[1];
+    tm.lap(tm_on, 1);
     if (reward_dev) {
         rc = bg_launch_reduce(gebv_dev, E, n * eng->T, reward_dev, 0, st);
         if (rc) return rc;
     }
-    tm.lap(3);
     bool sync = false;
     if (gebv_host) {
-        rc = copy_d2h(gebv_host, gebv_dev, (size_t)E * n * eng->T * sizeof(float), st);
+        rc = copy_d2h(eng, gebv_host, gebv_dev, (size_t)E * n * eng->T * sizeof(float), st);
         if (rc) return rc;
         sync = true;
     }
     if (reward_host) {
-        rc = copy_d2h(reward_host, reward_dev, (size_t)E * sizeof(float), st);
+        rc = copy_d2h(eng, reward_host, reward_dev, (size_t)E * sizeof(float), st);
         if (rc) return rc;
         sync = true;
     }
-    tm.lap(4);
+    tm.lap(tm_on, 2);
     if (sync) BG_CUDA(cudaStreamSynchronize(st));
-    tm.lap(5);
-    tm.done();
+    tm.lap(tm_on, 3);
+    tm.done(tm_on);
     return BG_OK;
 }
 

@@ -8,21 +8,48 @@
 
 #include "../../include/breedgym_b200.h"
 
-// Crossover masks of one cross key (vector env).  Two slots let the masks of step t+1 be generated
-// on a side stream while step t is still blending / scoring: masks depend on the key chain only.
-struct bg_mask_slot {
-    uint32_t *mask = nullptr, *mut = nullptr;
-    size_t cap = 0, mut_cap = 0;   // words
+// Crossover masks of up to BG_BATCH_MAX CONSECUTIVE cross keys of the simulator's key chain (vector env), generated
+// by ONE launch of the mask kernel.  Masks depend on the key chain only, so while the steps of one batch run, the
+// batch that continues the chain is generated on a side stream; three buffers rotate (in use / being generated / its
+// readers long gone).  A lookup is by key, so a reseed or an explicit-key call simply misses and regenerates.
+constexpr int BG_BATCH_MAX = 8;
+struct bg_mask_batch {
+    uint32_t *mask = nullptr, *mut = nullptr;   // [count][rows][Wpad]
+    size_t cap = 0, mut_cap = 0;                // words
     bool valid = false;
-    uint32_t key[2] = {0, 0};
+    int count = 0;
+    uint32_t keys[BG_BATCH_MAX][2] = {};
+    bool has_state = false;                     // state_after = the chain state after keys[count-1] was drawn
+    uint32_t state_after[2] = {0, 0};
     int layout = -1, schedule = -1;
     int64_t rows = 0;
-    cudaEvent_t ready = nullptr;   // recorded after the generating kernel
-    cudaEvent_t freed = nullptr;   // recorded after the last blend that read the slot
-    bool ready_set = false, freed_set = false;
+    cudaEvent_t ready = nullptr;                // recorded after the generating kernel
+    cudaEvent_t freed = nullptr;                // recorded behind the batch's readers when their stream changes / before a refill
+    bool freed_set = false;
+    cudaStream_t gen_stream = nullptr;          // stream the generating kernel ran on
+    cudaStream_t synced_stream = nullptr;       // stream that has already been made to wait for `ready`
+    cudaStream_t use_stream = nullptr;          // stream of the readers since the last `freed` record
+    bool used = false;
+    unsigned long long stamp = 0;               // last use (LRU choice of the buffer to refill)
 };
 
-constexpr int BG_MASK_SLOTS = 3;  // current step + two steps of lookahead
+constexpr int BG_MASK_BATCHES = 3;
+
+// behaviour switches, read ONCE (bg_engine_create: environment; bg_engine_set_option afterwards) -- nothing on the
+// step path calls getenv
+struct bg_options {
+    int fuse = 1;              // 0: blend + GEBV kernels instead of the fused step kernel (cross-checks)
+    int gebv_algo = 0;         // 0 auto, 1..3 as bg_gebv_algo
+    int lookahead = BG_BATCH_MAX;  // steps of masks generated ahead on the side stream (0: none)
+    int mask_nt = 128;         // threads of the small mask CTAs that run beside the step kernel
+    int mask_big_ctas = 0;     // diagnostics: full-size mask CTAs on the side stream
+    int blend_env_chunk = 8;
+    int copy_engine = 0;       // 1: never use the mapped-memory copy kernels
+    long long mapped_d2h_max = 32 * 1024;
+    long long tc_target_ctas = 0;  // 0: default
+    int timing = 0;
+    int gebv_digits = 0;       // 0: as many base-256 digits as the map needs; 8: always 8 (cross-checks)
+};
 
 struct bg_engine {
     int device = 0;
@@ -39,11 +66,14 @@ struct bg_engine {
     double *d_inv_scale = nullptr;    // [T] 2^-s_t
     signed char *d_wdig = nullptr;    // [tc_steps][tc_N/8][8][8][16] int8 base-256 digits in core-matrix order
     int64_t tc_steps = 0;             // 128-marker K steps (= Wpad / 4)
-    int32_t tc_N = 0;                 // 8*T rounded up to a multiple of 16 (0: tensor-core path unavailable)
+    int32_t tc_D = 0;                 // base-256 digits per effect (4..8, chosen per map by bg_engine_set_map)
+    int32_t tc_N = 0;                 // tc_D*T rounded up to a multiple of 16 (0: tensor-core path unavailable)
     // grow-only scratch
-    bg_mask_slot slots[BG_MASK_SLOTS];
-    int last_slot = BG_MASK_SLOTS - 1;
+    bg_options opt;
+    bg_mask_batch batches[BG_MASK_BATCHES];
+    unsigned long long use_clock = 0;
     cudaStream_t side = nullptr;        // lookahead stream
+    cudaEvent_t tmp_event = nullptr;
     uint32_t *d_mut = nullptr;          // mutation scratch of bg_meiosis_masks
     size_t mut_cap = 0;                 // words
     unsigned long long *d_acc = nullptr;
@@ -86,6 +116,8 @@ enum { BG_ROWS_MASK = 0, BG_ROWS_CROSS = 1, BG_ROWS_DH = 2 };
 int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_t cross_key[2], int layout, int schedule,
                            uint32_t *mask_out, uint32_t *mut_out, const uint32_t *pop, const int32_t *parents,
                            int64_t n_src, int64_t dh_offspring, uint32_t *out, cudaStream_t st, int small_ctas = 0);
+int bg_launch_mask_batch(bg_engine *eng, int64_t rows, int nkeys, const uint32_t (*keys)[2], int layout, int schedule,
+                         uint32_t *mask_out, uint32_t *mut_out, cudaStream_t st, int small_ctas);
 int bg_launch_blend(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask,
                     const uint32_t *mut, uint32_t *out, int64_t E, int64_t n_src, int64_t n, cudaStream_t st);
 
@@ -93,9 +125,6 @@ int bg_launch_blend(bg_engine *eng, const uint32_t *pop, const int32_t *parents,
 int bg_launch_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, int algo, cudaStream_t st);
 int bg_launch_reduce(const float *in, int64_t E, int64_t per_env, float *out, int op, cudaStream_t st);
 
-// gebv_tc.cu
-int bg_gebv_tc_max_traits(void);
-int bg_launch_gebv_tc(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st);
 // gebv_tc2.cu: TMA tile loads + operand A in tensor memory
 int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st, int scratch = 0);
 bool bg_cross_gebv_fused_ok(const bg_engine *eng, int64_t E, int64_t n_src, int64_t n);

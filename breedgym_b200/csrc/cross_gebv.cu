@@ -147,7 +147,7 @@ __device__ __forceinline__ uint32_t swz(int t, int q) { return (uint32_t)t * XG_
 // 8192 registers of the SM free -- exactly one 128-thread CTA of the mask kernel, which then runs in the issue slots
 // this (latency-bound) kernel leaves idle instead of displacing its CTAs
 __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
-    cross_gebv_kernel(const XGArgs fa, const int8_t *__restrict__ bdig, int N, int T, int nbp, int steps_total,
+    cross_gebv_kernel(const XGArgs fa, const int8_t *__restrict__ bdig, int N, int T, int D, int nbp, int steps_total,
                       int steps_per_split, unsigned long long *__restrict__ acc,
                       const double *__restrict__ inv_scale, float *__restrict__ out)
 {
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
     if (warp < 4) {
         mbar_wait(smem_u32(&bars.done), 0);
         if (tid == 0) XG_STAMP(15, 2);
-        digits_epilogue(tmem_d, tid, warp, row0, fa.rows, T, acc, inv_scale, out, gridDim.y, row_out);
+        digits_epilogue(tmem_d, tid, warp, row0, fa.rows, T, acc, inv_scale, out, gridDim.y, D, row_out);
     }
     if (tid == 0) XG_STAMP(15, 3);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -484,7 +484,8 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
     if (resident > XG_CTAS) resident = XG_CTAS;
     if (resident < 1) resident = 1;
     int ksplit, sps;
-    bg_tc_split(tiles, steps, 2LL * resident * eng->sm_count /* two waves */, XG_SPS, &ksplit, &sps);
+    bg_tc_split(tiles, steps, eng->opt.tc_target_ctas > 0 ? eng->opt.tc_target_ctas : 2LL * resident * eng->sm_count /* two waves */, XG_SPS,
+                &ksplit, &sps);
     int rc = bg_tc_reserve_scratch(eng, 0, rows * T, tiles, st);
     if (rc) return rc;
     if (smem > eng->tc2_optin[1]) {
@@ -502,7 +503,7 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
     fa.rows = rows;
     fa.W4 = eng->Wpad / 4;
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
-    cross_gebv_kernel<<<grid, XG_THREADS, smem, st>>>(fa, eng->d_wdig, N, T, nbp, steps, sps, eng->d_acc2[0],
+    cross_gebv_kernel<<<grid, XG_THREADS, smem, st>>>(fa, eng->d_wdig, N, T, eng->tc_D, nbp, steps, sps, eng->d_acc2[0],
                                                       eng->d_inv_scale, gebv_out);
     BG_LAUNCHED();
     return BG_OK;

@@ -123,16 +123,16 @@ __global__ void __launch_bounds__(256) reduce_env_kernel(const float *__restrict
 int bg_launch_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, int algo, cudaStream_t st)
 {
     BG_REQUIRE(eng && eng->d_wfix, BG_ESTATE, "engine has no map (call bg_engine_set_map)");
-    BG_REQUIRE(algo >= 0 && algo <= 4, BG_EINVAL, "bad GEBV algorithm id");
+    BG_REQUIRE(algo >= 0 && algo <= 3, BG_EINVAL, "bad GEBV algorithm id");
     if (rows == 0 || eng->T == 0) return BG_OK;
     const int T = eng->T;
     if (algo == 0) {
-        if (const char *s = getenv("BG_GEBV_ALGO")) algo = atoi(s);
-        if (algo < 1 || algo > 4) algo = eng->tc_N ? 3 : 2;
+        algo = eng->opt.gebv_algo;
+        if (algo < 1 || algo > 3) algo = eng->tc_N ? 3 : 2;
     }
-    if (algo >= 3) {
-        BG_REQUIRE(eng->tc_N, BG_ELIMIT, "tensor-core GEBV supports at most 32 traits");
-        return algo == 3 ? bg_launch_gebv_tc2(eng, pop, rows, out, st) : bg_launch_gebv_tc(eng, pop, rows, out, st);
+    if (algo == 3) {
+        BG_REQUIRE(eng->tc_N, BG_ELIMIT, "too many traits for the tensor-core GEBV (digits x traits <= 256)");
+        return bg_launch_gebv_tc2(eng, pop, rows, out, st);
     }
     const int64_t total = rows * T, mpad = (int64_t)((eng->Wpad + 7) / 8) * 256;  // = bg_engine wfix row stride
     int rc = bg_reserve_acc(eng, (size_t)total);

@@ -54,7 +54,7 @@ struct T2Bars {
 
 // smem: raw ring [T2_R][256 plane-rows][16 B], then B stages [T2_S][N/8][8 ki][8][16 B]
 __global__ void __launch_bounds__(T2_THREADS, 4)
-    gebv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, int64_t rows, const int8_t *__restrict__ bdig, int N, int T,
+    gebv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, int64_t rows, const int8_t *__restrict__ bdig, int N, int T, int D,
                     int steps_total, int steps_per_split, unsigned long long *__restrict__ acc,
                     const double *__restrict__ inv_scale, float *__restrict__ out)
 {
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
 
     if (warp < 4) {
         mbar_wait(smem_u32(&bars.done), 0);
-        digits_epilogue(tmem_d, tid, warp, row0, rows, T, acc, inv_scale, out, gridDim.y);
+        digits_epilogue(tmem_d, tid, warp, row0, rows, T, acc, inv_scale, out, gridDim.y, D);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -203,7 +203,6 @@ int bg_tc_reserve_scratch(bg_engine *eng, int scratch, int64_t total, int64_t ti
 // K split: about `target` CTAs, >= 8 steps each, <= 3000 steps each, a multiple of `multiple` steps per split
 void bg_tc_split(int64_t tiles, int steps, int64_t target, int multiple, int *ksplit_out, int *sps_out)
 {
-    if (const char *s = getenv("BG_TC_TARGET_CTAS")) target = atoll(s) > 0 ? atoll(s) : target;
     int ksplit = (int)(target / tiles);
     const int max_split = (steps + 7) / 8;
     if (ksplit > max_split) ksplit = max_split;
@@ -222,7 +221,7 @@ void bg_tc_split(int64_t tiles, int steps, int64_t target, int multiple, int *ks
 int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st, int scratch)
 {
     BG_REQUIRE(eng && eng->d_wdig, BG_ESTATE, "engine has no tensor-core digit table");
-    const int T = eng->T, N = eng->tc_N;
+    const int T = eng->T, N = eng->tc_N, D = eng->tc_D;
     const int steps = (int)eng->tc_steps;
     const int64_t tiles = (rows + T2_M - 1) / T2_M;
     BG_REQUIRE(tiles < (int64_t(1) << 31) && 2 * rows < (int64_t(1) << 31), BG_ELIMIT, "too many rows");
@@ -254,7 +253,8 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
     if (resident > 4) resident = 4;  // __launch_bounds__
     if (resident < 1) resident = 1;
     int ksplit, sps;
-    bg_tc_split(tiles, steps, (int64_t)resident * eng->sm_count /* one full wave */, 1, &ksplit, &sps);
+    bg_tc_split(tiles, steps, eng->opt.tc_target_ctas > 0 ? eng->opt.tc_target_ctas : (int64_t)resident * eng->sm_count /* one full wave */, 1,
+                &ksplit, &sps);
     int rc = bg_tc_reserve_scratch(eng, scratch, rows * T, tiles, st);
     if (rc) return rc;
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
@@ -277,7 +277,7 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
     const int8_t *bd = eng->d_wdig;
     const double *inv = eng->d_inv_scale;
     unsigned long long *acc = eng->d_acc2[scratch];
-    BG_CUDA(cudaLaunchKernelEx(&cfg, gebv_tc2_kernel, tmap, rows, bd, N, T, steps, sps, acc, inv, out));
+    BG_CUDA(cudaLaunchKernelEx(&cfg, gebv_tc2_kernel, tmap, rows, bd, N, T, D, steps, sps, acc, inv, out));
     BG_LAUNCHED();
     return BG_OK;
 }

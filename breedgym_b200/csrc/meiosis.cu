@@ -23,7 +23,7 @@ struct RowParams {
     const uint32_t *thr;
     uint32_t mut_thr;
     uint32_t m, W, Wpad;
-    uint32_t k0, k1;
+    uint32_t keys[BG_BATCH_MAX][2];  // mask mode: grid row g <-> gamete row g % rows of key g / rows (one launch per batch of keys)
     uint64_t rows;
     int schedule;
     int mode;
@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_ke
     uint32_t *S = smem;
     uint32_t *Mu = smem + (P.Wpad + 8);
     const uint32_t tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
-    const uint64_t q = blockIdx.x;
+    const uint64_t grow = blockIdx.x;                  // row of the output arrays
+    const uint32_t kb = (uint32_t)(grow / P.rows);      // which key of the batch (0 unless mask mode)
+    const uint64_t q = grow - (uint64_t)kb * P.rows;   // gamete row of that key
     const bool has_mut = P.mut_thr != 0;
     const uint32_t W = P.W, Wpad = P.Wpad, m = P.m;
 
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_ke
         if (has_mut) Mu[i] = 0;
     }
     // per-gamete key: #q of split(k, rows); S2 splits it again into (rec, mut)
-    const TfKey kc = tf_make_key(P.k0, P.k1);
+    const TfKey kc = tf_make_key(P.keys[kb][0], P.keys[kb][1]);
     const TfKey kq = tf_split_at(kc, q, P.rows, LAYOUT);
     TfKey krec = kq, kmut = kq;
     if (P.schedule == BG_SCHEDULE_S2) {
@@ -228,10 +230,10 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_ke
     const uint4 *S4 = reinterpret_cast<const uint4 *>(S);
     const uint4 *Mu4 = reinterpret_cast<const uint4 *>(Mu);
     if (P.mode == BG_ROWS_MASK) {
-        uint4 *mo = reinterpret_cast<uint4 *>(P.mask_out + q * Wpad);
+        uint4 *mo = reinterpret_cast<uint4 *>(P.mask_out + grow * Wpad);
         for (uint32_t v = tid; v < W4; v += NT) mo[v] = S4[v];
         if (has_mut) {
-            uint4 *uo = reinterpret_cast<uint4 *>(P.mut_out + q * Wpad);
+            uint4 *uo = reinterpret_cast<uint4 *>(P.mut_out + grow * Wpad);
             for (uint32_t v = tid; v < W4; v += NT) uo[v] = Mu4[v];
         }
         return;
@@ -314,15 +316,16 @@ __global__ void __launch_bounds__(256) blend_envs_kernel(const uint4 *__restrict
 
 }  // namespace
 
-int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_t cross_key[2], int layout, int schedule,
-                           uint32_t *mask_out, uint32_t *mut_out, const uint32_t *pop, const int32_t *parents,
-                           int64_t n_src, int64_t dh_offspring, uint32_t *out, cudaStream_t st, int small_ctas)
+static int launch_rows(bg_engine *eng, int mode, int64_t rows, int nkeys, const uint32_t (*keys)[2], int layout, int schedule,
+                       uint32_t *mask_out, uint32_t *mut_out, const uint32_t *pop, const int32_t *parents, int64_t n_src,
+                       int64_t dh_offspring, uint32_t *out, cudaStream_t st, int small_ctas)
 {
     BG_REQUIRE(eng && eng->d_thr, BG_ESTATE, "engine has no map (call bg_engine_set_map)");
     BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
     BG_REQUIRE(schedule == BG_SCHEDULE_S1 || schedule == BG_SCHEDULE_S2, BG_EINVAL, "bad key schedule");
     BG_REQUIRE(!(schedule == BG_SCHEDULE_S1 && eng->mut_thr), BG_EINVAL, "schedule S1 has no mutation key");
-    BG_REQUIRE(rows >= 0 && rows < (int64_t(1) << 31), BG_ELIMIT, "too many gamete rows");
+    BG_REQUIRE(nkeys >= 1 && nkeys <= BG_BATCH_MAX, BG_EINVAL, "bad mask batch size");
+    BG_REQUIRE(rows >= 0 && rows * nkeys < (int64_t(1) << 31), BG_ELIMIT, "too many gamete rows");
     if (rows == 0) return BG_OK;
     const bool has_mut = eng->mut_thr != 0;
     const size_t smem = (size_t)(eng->Wpad + 8) * 4 * (has_mut ? 2 : 1);
@@ -334,8 +337,10 @@ int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_
     P.m = (uint32_t)eng->m;
     P.W = (uint32_t)eng->W;
     P.Wpad = (uint32_t)eng->Wpad;
-    P.k0 = cross_key[0];
-    P.k1 = cross_key[1];
+    for (int b = 0; b < BG_BATCH_MAX; ++b) {
+        P.keys[b][0] = b < nkeys ? keys[b][0] : 0u;
+        P.keys[b][1] = b < nkeys ? keys[b][1] : 0u;
+    }
     P.rows = (uint64_t)rows;
     P.schedule = schedule;
     P.mode = mode;
@@ -348,18 +353,33 @@ int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_
     P.out = out;
     P.one = 1u;
     // small_ctas: 128-thread CTAs (8192 registers) for mask kernels that run beside the fused step kernel, see cross_gebv.cu
-    int small_nt = 128;
-    if (const char *e = getenv("BG_MASK_NT")) small_nt = atoi(e) >= 32 && atoi(e) <= 256 ? atoi(e) / 32 * 32 : small_nt;  // tuning
-    const int NT = eng->W <= 1024 ? (small_ctas ? small_nt : 256) : 1024;
+    const int NT = eng->W <= 1024 ? (small_ctas ? eng->opt.mask_nt : 256) : 1024;
     void (*kern)(RowParams);
     if (NT <= 256)
         kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 256> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 256>;
     else
         kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 1024> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 1024>;
     if (smem > 48 * 1024) BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)rows, NT, smem, st>>>(P);
+    kern<<<(unsigned)(rows * nkeys), NT, smem, st>>>(P);
     BG_LAUNCHED();
     return BG_OK;
+}
+
+int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_t cross_key[2], int layout, int schedule,
+                           uint32_t *mask_out, uint32_t *mut_out, const uint32_t *pop, const int32_t *parents,
+                           int64_t n_src, int64_t dh_offspring, uint32_t *out, cudaStream_t st, int small_ctas)
+{
+    const uint32_t keys[1][2] = {{cross_key[0], cross_key[1]}};
+    return launch_rows(eng, mode, rows, 1, keys, layout, schedule, mask_out, mut_out, pop, parents, n_src, dh_offspring, out, st,
+                       small_ctas);
+}
+
+// masks of `nkeys` cross keys in one launch: mask_out / mut_out [nkeys][rows][Wpad]
+int bg_launch_mask_batch(bg_engine *eng, int64_t rows, int nkeys, const uint32_t (*keys)[2], int layout, int schedule,
+                         uint32_t *mask_out, uint32_t *mut_out, cudaStream_t st, int small_ctas)
+{
+    return launch_rows(eng, BG_ROWS_MASK, rows, nkeys, keys, layout, schedule, mask_out, mut_out, nullptr, nullptr, 0, 0, nullptr, st,
+                       small_ctas);
 }
 
 int bg_launch_blend(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask,
@@ -374,8 +394,7 @@ int bg_launch_blend(bg_engine *eng, const uint32_t *pop, const int32_t *parents,
     const int tiles = (W4 + threads - 1) / threads;
     BG_REQUIRE(tiles <= 65535, BG_ELIMIT, "n_markers too large for the blend grid");
     // env chunk: enough CTAs for several waves, but >= 4 envs per CTA so the mask load is amortised
-    int chunk = 8;
-    if (const char *s = getenv("BG_BLEND_ENV_CHUNK")) chunk = atoi(s) > 0 ? atoi(s) : chunk;
+    int chunk = eng->opt.blend_env_chunk;
     int64_t zs = (E + chunk - 1) / chunk;
     if (zs > 65535) {
         chunk = (int)((E + 65534) / 65535);

@@ -163,7 +163,8 @@ __device__ __forceinline__ void mma_commit(uint32_t bar)
 constexpr int KSPLIT_MAX = 255;
 __device__ __forceinline__ void digits_epilogue(uint32_t tmem_d, int tid, int warp, int64_t row0, int64_t rows, int T,
                                                 unsigned long long *__restrict__ acc, const double *__restrict__ inv_scale,
-                                                float *__restrict__ out, unsigned nsplit, const uint32_t *out_row_map = nullptr)
+                                                float *__restrict__ out, unsigned nsplit, int D,
+                                                const uint32_t *out_row_map = nullptr)
 {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int64_t row = row0 + tid;  // accumulator slot; the result goes to row `orow` of `out`
@@ -173,12 +174,13 @@ __device__ __forceinline__ void digits_epilogue(uint32_t tmem_d, int tid, int wa
         uint32_t v[8];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                     : "r"(taddr + (uint32_t)(8 * t))
+                     : "r"(taddr + (uint32_t)(D * t))  // columns D*t .. D*t+7 (those past D belong to the next trait: ignored)
                      : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         unsigned long long sum = 0;  // modular arithmetic: the true total fits in int64
 #pragma unroll
-        for (int d = 7; d >= 0; --d) sum = (sum << 8) + (unsigned long long)(long long)(int32_t)v[d];
+        for (int d = 7; d >= 0; --d)
+            if (d < D) sum = (sum << 8) + (unsigned long long)(long long)(int32_t)v[d];
         long long total = (long long)sum >> 6;  // prescaled operand: every (partial) sum is exactly 64x
         if (row < rows) {
             bool complete = nsplit == 1;  // no K split: this CTA holds the whole sum

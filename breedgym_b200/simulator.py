@@ -88,6 +88,7 @@ class Simulator:
         backend=None,
         rng_layout: str = "legacy",
         key_schedule: str = "S2",
+        engine_options: Optional[dict] = None,
     ):
         if rng_layout not in _lib.LAYOUT_ID:
             raise ValueError(f"rng_layout must be one of {list(_lib.LAYOUT_ID)}")
@@ -140,6 +141,8 @@ class Simulator:
         self._engine = ctypes.c_void_p()
         lib = _lib.load()
         _lib.check(lib.bg_engine_create(self.device.index, ctypes.byref(self._engine)))
+        for name, value in (engine_options or {}).items():
+            self.set_option(name, value)
         eff = self.GEBV_model.marker_effects
         _lib.check(lib.bg_engine_set_map(self._engine, _lib.nptr(self.recombination_vec), _lib.nptr(eff),
                                          self.n_markers, eff.shape[1], self.mutation))
@@ -161,6 +164,10 @@ class Simulator:
             self._engine = None
 
     # ---- helpers ---------------------------------------------------------------
+    def set_option(self, name: str, value: int):
+        """Engine tuning / cross-check switch (`bg_engine_set_option`; none changes results)."""
+        _lib.check(_lib.load().bg_engine_set_option(self._engine, name.encode(), int(value)))
+
     def _stream(self):
         # raw handle of torch's current stream on this device (the Python Stream object costs ~9 us per call)
         return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(self._device_index))
@@ -305,9 +312,9 @@ class Simulator:
                                  "gebv_dev": torch.empty((n, T), dtype=torch.float32, device=self.device)}
         io["act_np"][...] = a
         out = self._empty_words(n)
-        k = np.ascontiguousarray(self._next_key(), dtype=np.uint32)
+        # the key chain (`random_key, k = split(random_key)`) advances inside the call
         _lib.check(_lib.load().bg_vec_step(self._engine, src.data_ptr(), out.data_ptr(), io["act_pin"], io["act_dev"].data_ptr(),
-                                           1, src.shape[0], n, _lib.nptr(k), None, self._layout_id, self._schedule_id,
+                                           1, src.shape[0], n, self._key_ptr, self._layout_id, self._schedule_id,
                                            io["gebv_dev"].data_ptr(), None, io["gebv_pin"], None, self._stream()))
         gebv = io["gebv_np"].copy()
         if self.GEBV_model.offset:

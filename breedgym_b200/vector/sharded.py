@@ -12,12 +12,14 @@ with E envs.  The only exchange is the all-gather of the per-env rewards
 """
 from __future__ import annotations
 
+import ctypes
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from .. import _lib
 from .vec_env import VecBreedGym
 
 
@@ -50,14 +52,60 @@ def allgather_rewards(local: torch.Tensor, counts: Sequence[int], group=None) ->
     return torch.cat([p[:c] for p, c in zip(parts, counts)])
 
 
+class RewardGather:
+    """The path's one collective through the C ABI (`bg_allgather_f32`: ncclAllGather on the step's own stream, no
+    host round trip; the communicator is created and warmed once).  `torch.distributed` is used only to hand NCCL's
+    unique id to the other ranks.  Equal shard sizes only (the sharded env pads otherwise through torch)."""
+
+    def __init__(self, simulator, world: int, rank: int, count: int, group=None):
+        lib = _lib.load()
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.check(lib.bg_comm_unique_id(_lib.nptr(ident)))
+        box = [ident.tobytes()]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = np.frombuffer(box[0], dtype=np.uint8).copy()
+        self._comm = ctypes.c_void_p()
+        _lib.check(lib.bg_comm_create(simulator._engine, _lib.nptr(ident), world, rank, ctypes.byref(self._comm)))
+        self._fn = lib.bg_allgather_f32
+        self._destroy = lib.bg_comm_destroy
+        self.world, self.count = world, count
+        self.device = simulator.device
+        self._stream = simulator._stream
+        # two receive buffers, alternating: the rewards of an episode stay valid while the next episode runs
+        self._out = [torch.empty(world * count, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self._out_ptr = [o.data_ptr() for o in self._out]
+        self._pos = 0
+
+    def __call__(self, local: torch.Tensor) -> torch.Tensor:
+        self._pos ^= 1
+        rc = self._fn(self._comm, local.data_ptr(), self._out_ptr[self._pos], self.count, self._stream())
+        if rc:
+            _lib.check(rc)
+        return self._out[self._pos]
+
+    def close(self):
+        if self._comm:
+            self._destroy(self._comm)
+            self._comm = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedVecBreedGym:
     """`VecBreedGym` with `total_envs` logical envs partitioned over the ranks of a process group.
 
     `step(actions)` takes THIS rank's actions `[count, n, 2]` and returns the local
-    observation handle with the rewards of ALL envs.
+    observation handle with the rewards of ALL envs.  `collective`: "native" = `bg_allgather_f32`
+    (NCCL through the C ABI, on the step's stream), "torch" = `torch.distributed` (gloo in the CPU
+    tests), "auto" = native when the group's backend is nccl and the shards are equal.
     """
 
-    def __init__(self, total_envs: int, group=None, device: Optional[int] = None, **kwargs):
+    def __init__(self, total_envs: int, group=None, device: Optional[int] = None, collective: str = "auto", **kwargs):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -68,6 +116,17 @@ class ShardedVecBreedGym:
             device = torch.cuda.current_device()
         self.env = VecBreedGym(num_envs=self.count, env_shard=(self.begin, total_envs), device=device, **kwargs)
         self.num_envs = total_envs
+        if collective not in ("auto", "native", "torch"):
+            raise ValueError("collective must be 'auto', 'native' or 'torch'")
+        equal = len(set(self.counts)) == 1
+        if collective == "auto":
+            collective = "native" if (self.world > 1 and equal and dist.get_backend(group) == "nccl") else "torch"
+        if collective == "native" and not equal:
+            raise ValueError("the native reward all-gather needs equal shard sizes")
+        self.collective = collective
+        self._gather = RewardGather(self.env.simulator, self.world, self.rank, self.count, group) \
+            if (collective == "native" and self.world > 1) else None
+        self._zeros = None
 
     def __getattr__(self, name):
         if name.startswith("_") or name == "env":
@@ -80,17 +139,28 @@ class ShardedVecBreedGym:
     def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
         return self.env.reset(seed=seed, options=options)
 
+    def gather_rewards(self, local: torch.Tensor) -> torch.Tensor:
+        """float32[count] on this rank's GPU -> float32[total_envs] on every rank (enqueued, not synchronised)."""
+        if self.world == 1:
+            return local
+        if self._gather is not None:
+            return self._gather(local)
+        return allgather_rewards(local, self.counts, self.group)
+
     def step(self, local_actions):
-        will_reward = self.env.reward_shaping or self.env.step_idx + 1 == self.env.num_generations
-        obs, rews, ter, tru, infos = self.env.step(local_actions)
+        env = self.env
+        will_reward = env.reward_shaping or env.step_idx + 1 == env.num_generations
+        obs, rews, ter, tru, infos = env.step(local_actions)
         on_device = isinstance(rews, torch.Tensor)  # info_device="device": rewards never leave the GPUs
         if will_reward:
-            local = rews if on_device else torch.from_numpy(np.ascontiguousarray(rews, dtype=np.float32)).to(self.env.device)
-            rews = allgather_rewards(local, self.counts, self.group)
+            local = rews if on_device else torch.from_numpy(np.ascontiguousarray(rews, dtype=np.float32)).to(env.device)
+            rews = self.gather_rewards(local)
             if not on_device:
                 rews = rews.cpu().numpy()
         elif on_device:
-            rews = torch.zeros(self.total_envs, dtype=torch.float32, device=self.env.device)
+            if self._zeros is None:
+                self._zeros = torch.zeros(self.total_envs, dtype=torch.float32, device=env.device)
+            rews = self._zeros
         else:
             rews = np.zeros(self.total_envs)
         ter = np.full(self.total_envs, bool(ter[0]) if len(ter) else False)

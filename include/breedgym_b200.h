@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_VERSION 100
+#define BG_VERSION 200
 
 #define BG_OK 0
 #define BG_EINVAL (-1)   /* bad argument */
@@ -80,6 +80,16 @@ int64_t bg_words_per_row(int64_t n_markers);
  * GEBV_model.marker_effects; breedgym/breedgym.py:36, vec_env.py:45). */
 int bg_engine_create(int device, bg_engine **out);
 int bg_engine_destroy(bg_engine *eng);
+/* Tuning / cross-check switches (none changes results).  bg_engine_create reads each once from the
+ * environment as BG_OPT_<NAME>; nothing on the step path calls getenv.
+ *   fuse (1)            0: bg_cross_gebv / bg_vec_step run blend + GEBV kernels instead of the fused one
+ *   gebv_algo (0)       default algorithm of bg_gebv, see bg_gebv_algo
+ *   gebv_digits (0)     base-256 digits of the tensor-core GEBV operand: 0 = as many as the map needs,
+ *                       4..8 fixed (set BEFORE bg_engine_set_map)
+ *   lookahead (8)       steps of crossover masks generated ahead of bg_vec_step on a side stream
+ *   mask_nt (128), mask_big_ctas (0), blend_env_chunk (8), tc_target_ctas (0 = auto),
+ *   copy_engine (0), mapped_d2h_max (32768), timing (0)      launch-shape / transfer tuning */
+int bg_engine_set_option(bg_engine *eng, const char *name, int64_t value);
 /* recomb: host float32[m] (already shifted / chromosome starts = 0.5);
  * effects: host float32[m][n_traits] row-major; mutation: chromax `mutation`. */
 int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects, int64_t n_markers,
@@ -143,14 +153,20 @@ int bg_meiosis_masks(bg_engine *eng, uint32_t *mask_out, int64_t rows, const uin
  * chromax: TraitModel.__call__ = dot(sum(pop,-1), effects) (+0 offset) as called
  * from Simulator.GEBV / GEBV_model (breedgym/breedgym.py:233, vec_env.py:132-134).
  * pop packed [rows][2][Wpad] -> out float32 [rows][n_traits].
- * Arithmetic: exact 64-bit fixed point of the float32 effects, one final rounding
- * to float32 (deterministic; differs from a float64 dot by < 1 ulp of float32). */
+ * Arithmetic: 64-bit fixed point of the float32 effects (scale chosen per map, see bg_gebv_digits),
+ * exact integer sums, one final rounding to float32: deterministic, order independent, identical
+ * across kernels; within 1 float32 ulp of a float64 dot for single-trait maps, within
+ * 2^-25 * sum|effects| + 1 ulp in general. */
 int bg_gebv(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, void *stream);
-/* bg_gebv with an explicit kernel choice (cross-checks, tuning, > 32 traits);
+/* bg_gebv with an explicit kernel choice (cross-checks, tuning, more traits than the tensor-core tile holds);
  * algorithm id: 0 auto, 1 direct bit-test, 2 byte-LUT, 3 tcgen05 int8 GEMM
- * (TMA loads, dosage operand in tensor memory), 4 tcgen05 int8 GEMM (operand staged in shared
- * memory).  All produce the same 64-bit integers. */
+ * (TMA loads, dosage operand in tensor memory).  All produce the same 64-bit integers. */
 int bg_gebv_algo(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, int algo, void *stream);
+
+/* base-256 int8 digits per marker effect in the tensor-core GEBV operand (4..8), chosen per map by
+ * bg_engine_set_map from the effects' range (TraitModel.marker_effects): the float32 effects are held
+ * in fixed point with a worst-case GEBV error <= 2^-25 * sum|effects| (one trait always gets all 8). */
+int bg_gebv_digits(bg_engine *eng);
 
 /* rews = np.max(infos["GEBV"], axis=(1,2))  (breedgym/vector/vec_env.py:97):
  * gebv float32 [E][per_env] -> out float32 [E] */
@@ -180,18 +196,39 @@ int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, cons
 /* ---- one-call vector-env step ------------------------------------------------
  * VecBreedGym.step hot path (breedgym/vector/vec_env.py:88-100) with host
  * buffers at the boundary: copies actions_host (int32 [E][n][2], pinned or
- * pageable) to `actions_dev`, runs cross -> GEBV (-> max reward), copies
- * gebv/reward back to the host buffers when non-NULL, and synchronises the stream
- * iff any device->host copy was requested.  next_cross_key (may be NULL) points to
- * uint32[4]: the keys the FOLLOWING two steps will pass as cross_key if nobody reseeds
- * in between (bg_key_chain_next out[2..5]): their masks are generated on an internal
- * side stream while this step runs (masks depend on the key chain only); a wrong guess
- * costs nothing but that work. */
+ * pageable; NULL = the actions are already in actions_dev) to `actions_dev`,
+ * advances the simulator's key chain IN PLACE (`key_state`: host uint32[2] =
+ * Simulator.random_key; chromax: `random_key, k = split(random_key)`), runs
+ * cross -> GEBV (-> max reward when reward_dev is non-NULL), copies gebv/reward
+ * back to the host buffers when non-NULL, and synchronises the stream iff any
+ * device->host copy was requested.  The crossover masks depend on the key chain
+ * only: the masks of the following steps (option `lookahead`) are generated by
+ * ONE kernel launch per batch of steps on an internal side stream while the
+ * current steps run; a reseed simply misses and regenerates. */
 int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_t *actions_host, int32_t *actions_dev,
-                int64_t E, int64_t n_src, int64_t n, const uint32_t cross_key[2], const uint32_t *next_cross_key,
-                int layout, int schedule,
+                int64_t E, int64_t n_src, int64_t n, uint32_t key_state[2], int layout, int schedule,
                 float *gebv_dev /* [E][n][T] */, float *reward_dev /* [E] or NULL */, float *gebv_host /* or NULL */,
                 float *reward_host /* or NULL */, void *stream);
+
+/* ---- reward all-gather (multi-GPU) ---------------------------------------------
+ * The ONE collective of the env-sharded path: every rank contributes float32[count]
+ * rewards, every rank receives float32[world * count] in rank order.  B200-native
+ * replacement for the observation/reward pipes of DistributedBreedGym
+ * (breedgym/vector/vec_env.py:197-219: step_async / step_wait through host
+ * subprocess pipes).  ncclAllGather over NVLink on the caller's stream: no host
+ * round trip, capturable, ordered behind the step that produced the rewards.
+ * NCCL (libnccl.so.2, the copy the process already has loaded -- torch's -- or the
+ * system one) is bound at run time with dlopen; without it bg_comm_* return BG_ESTATE.
+ *   rank 0: bg_comm_unique_id(id) -> broadcast the 128 bytes (any channel) -> every
+ *   rank: bg_comm_create(eng, id, world, rank, &comm)  (collective call).
+ * bg_comm_create runs one warm-up all-gather and synchronises, so the first timed
+ * collective does not pay NCCL's lazy channel setup. */
+typedef struct bg_comm bg_comm;
+#define BG_COMM_ID_BYTES 128
+int bg_comm_unique_id(uint8_t id_out[BG_COMM_ID_BYTES]);
+int bg_comm_create(bg_engine *eng, const uint8_t id[BG_COMM_ID_BYTES], int world, int rank, bg_comm **out);
+int bg_comm_destroy(bg_comm *comm);
+int bg_allgather_f32(bg_comm *comm, const float *send_dev, float *recv_dev, int64_t count, void *stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,7 @@ def load():
             _b.build()
         _lib = ctypes.CDLL(str(LIB_PATH))
         _lib.orc_cross_envs.restype = ctypes.c_int
+        _lib.orc_cross_envs_shared.restype = ctypes.c_int
         _lib.orc_num_threads.restype = ctypes.c_int
     return _lib
 
@@ -62,8 +63,10 @@ def split(key, num, layout="legacy"):
     return out
 
 
-def cross_envs(pops, actions, r, cross_key, mutation=0.0, schedule="S2", layout="legacy"):
-    """pops bool[E,N,m,2], actions int[E,n,2] -> bool[E,n,m,2]; one key for all envs."""
+def cross_envs(pops, actions, r, cross_key, mutation=0.0, schedule="S2", layout="legacy", shared_masks=False):
+    """pops bool[E,N,m,2], actions int[E,n,2] -> bool[E,n,m,2]; one key for all envs.
+    shared_masks: draw the 2n crossover masks once and reuse them for every env (how the reference's vmap runs)
+    instead of re-drawing per (env, gamete); same results."""
     pops = np.ascontiguousarray(pops, dtype=np.bool_)
     actions = np.ascontiguousarray(actions, dtype=np.int32)
     r = np.ascontiguousarray(r, dtype=np.float32)
@@ -71,7 +74,8 @@ def cross_envs(pops, actions, r, cross_key, mutation=0.0, schedule="S2", layout=
     E, N, m, _ = pops.shape
     n = actions.shape[1]
     out = np.empty((E, n, m, 2), dtype=np.bool_)
-    rc = load().orc_cross_envs(_p(pops), _p(actions), _p(r), ctypes.c_int64(E), ctypes.c_int64(N),
+    fn = load().orc_cross_envs_shared if shared_masks else load().orc_cross_envs
+    rc = fn(_p(pops), _p(actions), _p(r), ctypes.c_int64(E), ctypes.c_int64(N),
                                ctypes.c_int64(n), ctypes.c_int64(m), _p(cross_key), ctypes.c_float(mutation),
                                ctypes.c_int(SCHEDULE_ID[schedule]), ctypes.c_int(LAYOUT_ID[layout]), _p(out))
     if rc != 0:

@@ -155,6 +155,73 @@ int orc_cross_envs(const uint8_t *pops, const int32_t *actions, const float *r, 
     return err;
 }
 
+/* The same step the way the reference's vmap executes it (breedgym/vector/vec_env.py:75-77: `jax.vmap(
+ * simulator.cross, in_axes=(None, 0))` traces the key split and the uniform draws ONCE, outside the env axis): the
+ * 2n crossover masks are drawn once per step (byte per marker, as XLA materialises `cumxor(u < r)`), then every env
+ * only gathers and selects.  Same results as orc_cross_envs; this is the honest CPU baseline of the vector env
+ * (bench.py: cpu_baseline / --impl reference), orc_cross_envs re-draws per env (E x the Threefry work). */
+int orc_cross_envs_shared(const uint8_t *pops, const int32_t *actions, const float *r, int64_t E, int64_t N, int64_t n,
+                          int64_t m, const uint32_t cross_key[2], float mutation, int schedule, int layout, uint8_t *out)
+{
+    const int64_t rows = 2 * n;
+    uint32_t *keys = (uint32_t *)malloc(sizeof(uint32_t) * 2 * (size_t)rows);
+    uint8_t *mask = (uint8_t *)malloc((size_t)rows * (size_t)m);
+    uint8_t *mut = (mutation > 0.0f && schedule == SCHED_S2) ? (uint8_t *)malloc((size_t)rows * (size_t)m) : NULL;
+    if (!keys || !mask || ((mutation > 0.0f && schedule == SCHED_S2) && !mut)) {
+        free(keys); free(mask); free(mut);
+        return -1;
+    }
+    orc_split(cross_key, rows, layout, keys);
+    int err = 0;
+#pragma omp parallel
+    {
+        uint32_t *scratch = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(m + 1));
+        if (!scratch) {
+#pragma omp atomic write
+            err = -1;
+        } else {
+#pragma omp for schedule(dynamic, 4)
+            for (int64_t q = 0; q < rows; ++q) {
+                uint32_t krec[2] = {keys[2 * q], keys[2 * q + 1]}, kmut[2] = {0, 0};
+                if (schedule == SCHED_S2) {
+                    uint32_t ks[4];
+                    orc_split(&keys[2 * q], 2, layout, ks);
+                    krec[0] = ks[0]; krec[1] = ks[1];
+                    kmut[0] = ks[2]; kmut[1] = ks[3];
+                }
+                orc_random_bits(krec, m, layout, scratch);
+                uint8_t c = 0;
+                for (int64_t j = 0; j < m; ++j) {
+                    c ^= (uint8_t)(bits_to_uniform(scratch[j]) < r[j]);
+                    mask[q * m + j] = c;
+                }
+                if (mut) {
+                    orc_random_bits(kmut, m, layout, scratch);
+                    for (int64_t j = 0; j < m; ++j) mut[q * m + j] = (uint8_t)(bits_to_uniform(scratch[j]) < mutation);
+                }
+            }
+#pragma omp for schedule(static) collapse(2)
+            for (int64_t e = 0; e < E; ++e)
+                for (int64_t q = 0; q < rows; ++q) {
+                    const int64_t i = q >> 1, p = q & 1;
+                    const int64_t a = norm_index(actions[(e * n + i) * 2 + p], N);
+                    const uint8_t *ind = pops + ((e * N + a) * m) * 2;
+                    uint8_t *o = out + ((e * n + i) * m) * 2 + p;
+                    const uint8_t *mk = mask + q * m;
+                    if (mut) {
+                        const uint8_t *mu = mut + q * m;
+                        for (int64_t j = 0; j < m; ++j) o[2 * j] = ind[2 * j + mk[j]] ^ mu[j];
+                    } else {
+                        for (int64_t j = 0; j < m; ++j) o[2 * j] = ind[2 * j + mk[j]];
+                    }
+                }
+            free(scratch);
+        }
+    }
+    free(keys); free(mask); free(mut);
+    return err;
+}
+
 /* TraitModel.__call__ in float64: pop bool[rows][m][2], effects f32[m][T] -> out f64[rows][T] */
 void orc_gebv(const uint8_t *pop, const float *effects, int64_t rows, int64_t m, int64_t T, double *out)
 {

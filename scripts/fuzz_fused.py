@@ -45,13 +45,12 @@ for case in range(n_cases):
     for no_fuse in (False, True):
         out = torch.zeros((E, n, 2, W), dtype=torch.int32, device=dev)
         gebv = torch.zeros((E, n, T), dtype=torch.float32, device=dev)
-        if no_fuse:
-            os.environ["BG_NO_FUSE"] = "1"
+        sim.set_option("fuse", 0 if no_fuse else 1)
         try:
             _lib.check(lib.bg_cross_gebv(sim._engine, pop.data_ptr(), acts.data_ptr(), out.data_ptr(), E, n_src, n, _lib.nptr(key),
                                          sim._layout(), sim._schedule(), gebv.data_ptr(), sim._stream()))
         finally:
-            os.environ.pop("BG_NO_FUSE", None)
+            sim.set_option("fuse", 1)
         torch.cuda.synchronize()
         res.append((out, gebv))
     ok = torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

@@ -411,14 +411,14 @@ def test_sharded_env_over_nccl_matches_unsharded(cuda_device):
     assert "multi-gpu check ok" in r.stdout
 
 
-def test_reset_infos_gathered_from_germplasm_equal_rescored(cuda_device, monkeypatch):
+def test_reset_infos_gathered_from_germplasm_equal_rescored(cuda_device):
     """VecBreedGym.reset gathers the reset infos from the germplasm's GEBVs (a GEBV is a function of the individual
-    alone); re-scoring the drawn populations (BG_NO_GERM_GEBV=1, what vec_env.py:130 does) gives the same bits."""
+    alone); re-scoring the drawn populations (reuse_germplasm_gebv=False, what vec_env.py:130 does) gives the same bits."""
     kw = dict(num_envs=5, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=37)
     env_a = gym().make("VecBreedGym", **kw)
     pop_a, infos_a = env_a.reset(seed=11)
-    monkeypatch.setenv("BG_NO_GERM_GEBV", "1")
     env_b = gym().make("VecBreedGym", **kw)
+    env_b.reuse_germplasm_gebv = False
     pop_b, infos_b = env_b.reset(seed=11)
     assert env_a._germ_gebv is not None and env_b._germ_gebv is None
     assert np.array_equal(np.asarray(pop_a), np.asarray(pop_b))
@@ -472,13 +472,11 @@ def test_vec_reseed_mid_episode_discards_lookahead_masks(cuda_device):
         assert np.allclose(infos["GEBV"], cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)
 
 
-def test_vec_device_mode_prefetched_autoreset_matches_oracle(cuda_device, monkeypatch):
-    """info_device="device" with BG_RESET_PREFETCH=1 (opt-in): the next reset is drawn ahead of time on a side stream and
-    adopted at the autoreset; the trajectory across two autoresets must equal the oracle's, and a reseed must discard
-    the prefetched draw."""
+def test_vec_device_mode_ring_autoreset_matches_oracle(cuda_device):
+    """info_device="device": observations / infos cycle through the preallocated ring (no allocation per step); the
+    trajectory across two autoresets and a reseed in the middle of an episode (the mask lookahead then misses and
+    regenerates) must equal the oracle's, and a handle must stay valid for one further step."""
     import torch
-
-    monkeypatch.setenv("BG_RESET_PREFETCH", "1")
 
     num_envs, n = 3, 60
     env = gym().make("VecBreedGym", num_envs=num_envs, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n,
@@ -487,13 +485,16 @@ def test_vec_device_mode_prefetched_autoreset_matches_oracle(cuda_device, monkey
     rng = np.random.default_rng(2)
     for seed in (7, 8):
         pop, infos = env.reset(seed=seed)
-        assert env._prefetched is not None
         osim = oracle_sim(env.simulator, seed)
         okey, opops, _ = cr.vec_reset(germ, n, num_envs, jp.key(seed), "legacy")
         assert np.array_equal(np.asarray(pop), opops)
         for step in range(7):
             action = rng.integers(0, n, (num_envs, n, 2))
+            prev_words, prev_ref = pop.words, opops
             pop, rews, ter, tru, infos = env.step(torch.from_numpy(action).to(cuda_device))
+            # the previous observation's buffer is still intact one step later (ring of 3)
+            from breedgym_b200.population import PackedPopulation
+            assert np.array_equal(np.asarray(PackedPopulation(env.simulator, prev_words)), prev_ref)
             opops = cr.vec_step(osim, opops, action)
             assert np.allclose(infos["GEBV"].cpu().numpy(), cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)
             if step % 3 == 2:  # autoreset: the returned population is the next episode's first
