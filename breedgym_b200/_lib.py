@@ -44,7 +44,7 @@ _SIGNATURES = {
     "bg_cross": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "bg_cross_gebv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p,
                               c_void_p]),
-    "bg_double_haploid": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p]),
+    "bg_double_haploid": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "bg_meiosis_masks": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "bg_gebv": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "bg_gebv_algo": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),

@@ -8,7 +8,6 @@ fuses the parent gather into the meiosis kernel.
 """
 from __future__ import annotations
 
-from math import ceil, floor, sqrt
 from pathlib import Path
 from typing import Optional, Tuple, Union
 
@@ -149,44 +148,15 @@ class BreedGym(Env):
             self._corrcoef_cache = True
         return self._corrcoef
 
-    # ---- rendering (matplotlib is optional; imported lazily) ---------------------
-    def _plt(self):
-        try:
-            import matplotlib.pyplot as plt
-        except ImportError as e:  # pragma: no cover
-            raise ImportError("render_mode='matplotlib' needs matplotlib") from e
-        return plt
-
+    # ---- rendering: out of scope -- the constructor arguments are accepted for drop-in
+    # compatibility, the plotting itself (breedgym/breedgym.py:159-222 of the reference) is not part of the hot path
     def _make_axs(self):
-        if "axs" in self.render_kwargs:
-            return self.render_kwargs["axs"]
-        n_figs = len(self.render_kwargs["traits"]) + len(self.render_kwargs["other_features"])
-        nrows = floor(sqrt(n_figs))
-        ncols = ceil(n_figs / nrows)
-        axs = self._plt().subplots(nrows, ncols, figsize=(4 * ncols, 4 * nrows))[1]
-        return np.asarray(axs).flatten()
+        return self.render_kwargs.get("axs")
 
     def _render_step(self, info: dict):
-        plt = self._plt()
-        color = self.render_kwargs["colors"][self.episode_idx % len(self.render_kwargs["colors"])]
-        series = [info["GEBV"][t] for t in self.render_kwargs["traits"]]
-        series += [f() for f in self.render_kwargs["other_features"]]
-        for ax, values in zip(self.axs, series):
-            bp = ax.boxplot(values, positions=[self.step_idx + self.episode_idx / 6], flierprops={"markersize": 2})
-            plt.setp(bp.values(), color=color)
+        pass
 
     def render(self, file_name: Optional[Union[str, Path]] = None):
-        if self.render_mode is None:
-            return
-        plt = self._plt()
-        xticks = np.arange(self.step_idx + 1)
-        titles = list(self.render_kwargs["traits"]) + list(self.render_kwargs["feature_names"])
-        for ax, title in zip(self.axs, titles):
-            ax.set_xticks(xticks + self.episode_idx / 12, xticks)
-            ax.set_title(title)
-            ax.grid(axis="y")
-            ax.set_xlabel("Generations [Years]")
-        plt.tight_layout()
-        if file_name is not None:
-            plt.savefig(file_name, bbox_inches="tight")
-        plt.show()
+        if self.render_mode is not None:
+            raise NotImplementedError("breedgym_b200 does not render: plot env.GEBV / env.corrcoef with the reference's "
+                                      "matplotlib code (breedgym/breedgym.py:159-222) if needed")

@@ -644,15 +644,14 @@ int bg_blend_envs(bg_engine *eng, const uint32_t *pop, const int32_t *parents, c
     return bg_launch_blend(eng, pop, parents, mask, mut, out, E, n_src, n, (cudaStream_t)stream);
 }
 
-int bg_double_haploid(bg_engine *eng, const uint32_t *pop, uint32_t *out, int64_t n, int64_t n_offspring,
+int bg_double_haploid(bg_engine *eng, const uint32_t *pop, uint32_t *out, int64_t E, int64_t n, int64_t n_offspring,
                       const uint32_t cross_key[2], int layout, int schedule, void *stream)
 {
     BG_ENTER(eng);
-    BG_REQUIRE(n >= 0 && n_offspring >= 0 && cross_key, BG_EINVAL, "bg_double_haploid: bad shape");
-    if (n * n_offspring == 0) return BG_OK;
+    BG_REQUIRE(E >= 0 && n >= 0 && n_offspring >= 0 && cross_key, BG_EINVAL, "bg_double_haploid: bad shape");
+    if (E * n * n_offspring == 0) return BG_OK;
     BG_REQUIRE(pop && out, BG_EINVAL, "bg_double_haploid: null buffer");
-    return bg_launch_meiosis_rows(eng, BG_ROWS_DH, n * n_offspring, cross_key, layout, schedule, nullptr, nullptr, pop, nullptr, n,
-                                  n_offspring, out, (cudaStream_t)stream);
+    return bg_launch_double_haploid(eng, E, n, n_offspring, cross_key, layout, schedule, pop, out, (cudaStream_t)stream);
 }
 
 int bg_meiosis_masks(bg_engine *eng, uint32_t *mask_out, int64_t rows, const uint32_t cross_key[2], int layout, int schedule,

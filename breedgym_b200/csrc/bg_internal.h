@@ -116,6 +116,8 @@ enum { BG_ROWS_MASK = 0, BG_ROWS_CROSS = 1, BG_ROWS_DH = 2 };
 int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_t cross_key[2], int layout, int schedule,
                            uint32_t *mask_out, uint32_t *mut_out, const uint32_t *pop, const int32_t *parents,
                            int64_t n_src, int64_t dh_offspring, uint32_t *out, cudaStream_t st, int small_ctas = 0);
+int bg_launch_double_haploid(bg_engine *eng, int64_t E, int64_t n, int64_t n_offspring, const uint32_t cross_key[2], int layout,
+                             int schedule, const uint32_t *pop, uint32_t *out, cudaStream_t st);
 int bg_launch_mask_batch(bg_engine *eng, int64_t rows, int nkeys, const uint32_t (*keys)[2], int layout, int schedule,
                          uint32_t *mask_out, uint32_t *mut_out, cudaStream_t st, int small_ctas);
 int bg_launch_blend(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask,

@@ -25,6 +25,7 @@ struct RowParams {
     uint32_t m, W, Wpad;
     uint32_t keys[BG_BATCH_MAX][2];  // mask mode: grid row g <-> gamete row g % rows of key g / rows (one launch per batch of keys)
     uint64_t rows;
+    uint32_t same_key;  // 1: every group of `rows` grid rows uses keys[0] (double haploids of E envs under ONE key)
     int schedule;
     int mode;
     uint32_t *mask_out;
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_ke
         if (has_mut) Mu[i] = 0;
     }
     // per-gamete key: #q of split(k, rows); S2 splits it again into (rec, mut)
-    const TfKey kc = tf_make_key(P.keys[kb][0], P.keys[kb][1]);
+    const uint32_t ki = P.same_key ? 0u : kb;
+    const TfKey kc = tf_make_key(P.keys[ki][0], P.keys[ki][1]);
     const TfKey kq = tf_split_at(kc, q, P.rows, LAYOUT);
     TfKey krec = kq, kmut = kq;
     if (P.schedule == BG_SCHEDULE_S2) {
@@ -243,9 +245,9 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_ke
     if (P.mode == BG_ROWS_CROSS) {
         src = norm_index(P.parents[q], P.n_src);
         dst0 = reinterpret_cast<uint4 *>(P.out + q * Wpad);
-    } else {  // double haploid: the gamete fills both planes of individual q
-        src = (int64_t)(q / (uint64_t)P.dh_offspring);
-        dst0 = reinterpret_cast<uint4 *>(P.out + (2 * q) * Wpad);
+    } else {  // double haploid: the gamete fills both planes of individual `grow` (env-major: env = grow / rows)
+        src = (int64_t)(grow / (uint64_t)P.dh_offspring);
+        dst0 = reinterpret_cast<uint4 *>(P.out + (2 * grow) * Wpad);
         dst1 = dst0 + W4;
     }
     const uint4 *h0 = reinterpret_cast<const uint4 *>(P.pop + (uint64_t)(2 * src) * Wpad);
@@ -318,14 +320,16 @@ __global__ void __launch_bounds__(256) blend_envs_kernel(const uint4 *__restrict
 
 static int launch_rows(bg_engine *eng, int mode, int64_t rows, int nkeys, const uint32_t (*keys)[2], int layout, int schedule,
                        uint32_t *mask_out, uint32_t *mut_out, const uint32_t *pop, const int32_t *parents, int64_t n_src,
-                       int64_t dh_offspring, uint32_t *out, cudaStream_t st, int small_ctas)
+                       int64_t dh_offspring, uint32_t *out, cudaStream_t st, int small_ctas, int64_t groups = 0)
 {
+    // groups > 0: `groups` x rows grid rows, every group under keys[0] (nkeys == 1)
+    const int64_t grid_groups = groups > 0 ? groups : nkeys;
     BG_REQUIRE(eng && eng->d_thr, BG_ESTATE, "engine has no map (call bg_engine_set_map)");
     BG_REQUIRE(layout == BG_LAYOUT_LEGACY || layout == BG_LAYOUT_PARTITIONABLE, BG_EINVAL, "bad PRNG layout");
     BG_REQUIRE(schedule == BG_SCHEDULE_S1 || schedule == BG_SCHEDULE_S2, BG_EINVAL, "bad key schedule");
     BG_REQUIRE(!(schedule == BG_SCHEDULE_S1 && eng->mut_thr), BG_EINVAL, "schedule S1 has no mutation key");
     BG_REQUIRE(nkeys >= 1 && nkeys <= BG_BATCH_MAX, BG_EINVAL, "bad mask batch size");
-    BG_REQUIRE(rows >= 0 && rows * nkeys < (int64_t(1) << 31), BG_ELIMIT, "too many gamete rows");
+    BG_REQUIRE(rows >= 0 && rows * grid_groups < (int64_t(1) << 31), BG_ELIMIT, "too many gamete rows");
     if (rows == 0) return BG_OK;
     const bool has_mut = eng->mut_thr != 0;
     const size_t smem = (size_t)(eng->Wpad + 8) * 4 * (has_mut ? 2 : 1);
@@ -342,6 +346,7 @@ static int launch_rows(bg_engine *eng, int mode, int64_t rows, int nkeys, const 
         P.keys[b][1] = b < nkeys ? keys[b][1] : 0u;
     }
     P.rows = (uint64_t)rows;
+    P.same_key = groups > 0 ? 1u : 0u;
     P.schedule = schedule;
     P.mode = mode;
     P.mask_out = mask_out;
@@ -360,7 +365,7 @@ static int launch_rows(bg_engine *eng, int mode, int64_t rows, int nkeys, const 
     else
         kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 1024> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 1024>;
     if (smem > 48 * 1024) BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)(rows * nkeys), NT, smem, st>>>(P);
+    kern<<<(unsigned)(rows * grid_groups), NT, smem, st>>>(P);
     BG_LAUNCHED();
     return BG_OK;
 }
@@ -372,6 +377,15 @@ int bg_launch_meiosis_rows(bg_engine *eng, int mode, int64_t rows, const uint32_
     const uint32_t keys[1][2] = {{cross_key[0], cross_key[1]}};
     return launch_rows(eng, mode, rows, 1, keys, layout, schedule, mask_out, mut_out, pop, parents, n_src, dh_offspring, out, st,
                        small_ctas);
+}
+
+// double haploids of E populations [E][n][2][Wpad] under ONE key: out [E][n][n_offspring][2][Wpad]
+int bg_launch_double_haploid(bg_engine *eng, int64_t E, int64_t n, int64_t n_offspring, const uint32_t cross_key[2], int layout,
+                             int schedule, const uint32_t *pop, uint32_t *out, cudaStream_t st)
+{
+    const uint32_t keys[1][2] = {{cross_key[0], cross_key[1]}};
+    return launch_rows(eng, BG_ROWS_DH, n * n_offspring, 1, keys, layout, schedule, nullptr, nullptr, pop, nullptr, n, n_offspring, out,
+                       st, 0, E);
 }
 
 // masks of `nkeys` cross keys in one launch: mask_out / mut_out [nkeys][rows][Wpad]

@@ -18,8 +18,12 @@ from . import _lib
 
 
 def _is_int_index(idx) -> bool:
-    if isinstance(idx, (list, tuple)):
-        idx = np.asarray(idx)
+    """A single integer ARRAY index (list / ndarray / tensor).  Tuples are multi-axis indices, handled separately."""
+    if isinstance(idx, list):
+        try:
+            idx = np.asarray(idx)
+        except ValueError:
+            return False
     if isinstance(idx, torch.Tensor):
         return not (idx.dtype.is_floating_point or idx.dtype == torch.bool)
     return isinstance(idx, np.ndarray) and idx.dtype.kind in "iu"
@@ -111,6 +115,20 @@ class PackedPopulation:
             return PackedPopulation(self.sim, self.words[i])
         if isinstance(idx, slice):
             return PackedPopulation(self.sim, self.words[idx])
+        if isinstance(idx, tuple):
+            # multi-axis index.  The reference's vector-env idiom `populations[arange(E)[:, None, None], actions]`
+            # (breedgym/vector/vec_env.py:89-90, breeding_programs_env.py) is kept lazy: a per-env parents view that
+            # `Simulator.cross` hands to the kernel as index pairs; everything else is plain numpy indexing.
+            if len(idx) == 2 and self.words.dim() == 4:
+                env_ix, act = idx
+                act_a = act if isinstance(act, torch.Tensor) else np.asarray(act)
+                env_a = np.asarray(env_ix.cpu() if isinstance(env_ix, torch.Tensor) else env_ix)
+                E = self.words.shape[0]
+                if (act_a.ndim == 3 and act_a.shape[0] == E and act_a.shape[2] == 2 and _is_int_index(act_a)
+                        and env_a.shape == (E, 1, 1) and np.array_equal(env_a.ravel(), np.arange(E))):
+                    return ParentsView(self, act_a)
+            idx = tuple(i.cpu().numpy() if isinstance(i, torch.Tensor) else i for i in idx)
+            return self.numpy()[idx]
         if _is_int_index(idx) and self.words.dim() == 3:
             ia = idx if isinstance(idx, torch.Tensor) else np.asarray(idx)
             if ia.ndim == 1:
@@ -135,14 +153,20 @@ class ParentsView:
 
     @property
     def shape(self):
-        return (len(self.pairs), 2) + self.population.shape[-2:]
+        return tuple(self.pairs.shape) + self.population.shape[-2:]
 
     def __len__(self):
         return len(self.pairs)
 
     def __array__(self, dtype=None, copy=None):
         pairs = self.pairs.cpu().numpy() if isinstance(self.pairs, torch.Tensor) else np.asarray(self.pairs)
-        n = len(self.population)
-        pairs = np.clip(np.where(pairs < 0, pairs + n, pairs), 0, n - 1)
-        a = self.population.numpy()[pairs]
+        pop = self.population.numpy()
+        if pairs.ndim == 3:  # per-env view: populations[arange(E)[:, None, None], actions] -> [E, n, 2, m, 2]
+            n = pop.shape[1]
+            pairs = np.clip(np.where(pairs < 0, pairs + n, pairs), 0, n - 1)
+            a = pop[np.arange(pop.shape[0])[:, None, None], pairs]
+        else:
+            n = len(self.population)
+            pairs = np.clip(np.where(pairs < 0, pairs + n, pairs), 0, n - 1)
+            a = pop[pairs]
         return a if dtype is None else a.astype(dtype)

@@ -333,17 +333,20 @@ class Simulator:
         return self._cross_indexed(populations, actions, self._next_key())
 
     def double_haploid(self, population, n_offspring: int = 1) -> PackedPopulation:
+        """`(n, m, 2)` -> `(n, n_offspring, m, 2)` (squeezed for one offspring); a batch `(E, n, m, 2)` is the
+        reference's `vmap(double_haploid, in_axes=(None, 0))`: ONE key for all envs, one launch."""
         pop = self.as_packed(population)
-        if pop.words.dim() != 3:
-            raise ValueError("double_haploid expects one population (n, m, 2)")
+        if pop.words.dim() not in (3, 4):
+            raise ValueError("double_haploid expects one population (n, m, 2) or a batch (E, n, m, 2)")
         k = np.ascontiguousarray(self._next_key(), dtype=np.uint32)
-        n = len(pop)
-        out = self._empty_words(n, n_offspring)
-        _lib.check(_lib.load().bg_double_haploid(self._engine, pop.words.contiguous().data_ptr(), out.data_ptr(), n,
+        lead = tuple(pop.words.shape[:-2])
+        E, n = (1, lead[0]) if len(lead) == 1 else lead
+        out = self._empty_words(*lead, n_offspring)
+        _lib.check(_lib.load().bg_double_haploid(self._engine, pop.words.contiguous().data_ptr(), out.data_ptr(), E, n,
                                                  n_offspring, _lib.nptr(k), self._layout(), self._schedule(),
                                                  self._stream()))
         if n_offspring == 1:
-            out = out[:, 0]
+            out = out.squeeze(-3)
         return PackedPopulation(self, out)
 
     def GEBV(self, population) -> pd.DataFrame:

@@ -55,14 +55,10 @@ class WheatBreedGym(VectorWrapper):
         pop = self.cross(pairs)  # [E, n_lines]
         assert pop.shape[1] == self.n_lines
 
-        # double haploids: one key for all envs
-        k = np.ascontiguousarray(sim._next_key(), dtype=np.uint32)
-        dh = sim._empty_words(E, self.n_lines, self.plant_per_line)
-        lib = _lib.load()
-        for e in range(E):
-            _lib.check(lib.bg_double_haploid(sim._engine, pop.words[e].contiguous().data_ptr(), dh[e].data_ptr(),
-                                             self.n_lines, self.plant_per_line, _lib.nptr(k), sim._layout(),
-                                             sim._schedule(), sim._stream()))
+        # double haploids: one key for all envs, one launch (vmap(simulator.double_haploid, in_axes=(None, 0)))
+        dh = sim.double_haploid(pop, n_offspring=self.plant_per_line).words
+        if dh.dim() == 4:  # plant_per_line == 1 comes back squeezed
+            dh = dh.unsqueeze(2)
         W = sim.words_per_row
         # best k_per_line of every line
         lines = dh.reshape(E * self.n_lines, self.plant_per_line, 2, W)

@@ -31,7 +31,7 @@ import torch
 
 from .. import _lib
 from ..gym_compat import VectorEnv, spaces
-from ..population import PackedPopulation
+from ..population import PackedPopulation, ParentsView
 from ..simulator import Simulator
 from ..utils.paths import DATA_PATH
 
@@ -185,9 +185,13 @@ class VecBreedGym(VectorEnv):
         return pop.words
 
     # ---- the hot path ----------------------------------------------------------------
-    def cross(self, parents_idx) -> PackedPopulation:
-        """Offspring of `populations[arange, parents_idx]`, one key for all envs (vec_env.py:75-77)."""
-        return self.simulator.cross_envs(self.populations, parents_idx)
+    def cross(self, parents) -> PackedPopulation:
+        """Offspring of `populations[arange, parents_idx]`, one key for all envs (vec_env.py:75-77).  Takes the index
+        pairs `int[E, n, 2]`, or the lazy view the reference's idiom `populations[arange(E)[:, None, None], actions]`
+        returns here."""
+        if isinstance(parents, ParentsView):
+            return self.simulator.cross(parents)
+        return self.simulator.cross_envs(self.populations, parents)
 
     def step(self, actions):
         sim, E = self.simulator, self.num_envs

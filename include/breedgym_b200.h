@@ -137,11 +137,11 @@ int bg_cross_gebv(bg_engine *eng, const uint32_t *pop, const int32_t *parents, u
 int bg_blend_envs(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, const uint32_t *mut,
                   uint32_t *out, int64_t E, int64_t n_src, int64_t n, void *stream);
 
-/* chromax: Simulator.double_haploid / functional.double_haploid
- * (breedgym/vector/breeding_programs_env.py:41).  pop packed [n][2][Wpad] ->
- * out packed [n][n_offspring][2][Wpad], both planes = the gamete of key
- * #(i*n_offspring+o) of split(k, n*n_offspring). */
-int bg_double_haploid(bg_engine *eng, const uint32_t *pop, uint32_t *out, int64_t n, int64_t n_offspring,
+/* chromax: Simulator.double_haploid / functional.double_haploid, and its vmap over envs under ONE key
+ * (breedgym/vector/breeding_programs_env.py:39-41: `vmap(simulator.double_haploid, in_axes=(None, 0))`).
+ * pop packed [E][n][2][Wpad] -> out packed [E][n][n_offspring][2][Wpad], both planes = the gamete of key
+ * #(i*n_offspring+o) of split(k, n*n_offspring), the same keys for every env; E = 1: one population. */
+int bg_double_haploid(bg_engine *eng, const uint32_t *pop, uint32_t *out, int64_t E, int64_t n, int64_t n_offspring,
                       const uint32_t cross_key[2], int layout, int schedule, void *stream);
 
 /* crossover masks only (tests / diagnostics): mask_out [rows][Wpad], inclusive

@@ -45,6 +45,27 @@ def main():
         assert np.array_equal(infos_s["GEBV"], infos_f["GEBV"][sl]), f"step {step}: GEBV differs"
         assert rs.shape == (total,) and np.array_equal(rs, rf), f"step {step}: gathered rewards differ"
         assert np.array_equal(ts, tf)
+    # equal shards: the reward all-gather goes through the C ABI (bg_allgather_f32 = ncclAllGather on the step's stream),
+    # device-resident infos, observation ring; compared with the unsharded env on the same GPU
+    total2 = 3 * world
+    shard2 = ShardedVecBreedGym(total_envs=total2, device=local, info_device="device", **kw)
+    assert shard2.collective == "native", shard2.collective
+    full2 = VecBreedGym(num_envs=total2, device=local, info_device="device", **kw)
+    shard2.reset(seed=5)
+    full2.reset(seed=5)
+    sl2 = shard2.local_slice()
+    dev = torch.device("cuda", local)
+    for step in range(9):
+        act = rng.integers(0, n, (total2, n, 2)).astype(np.int32)
+        ps, rs, _, ts, infos_s = shard2.step(torch.from_numpy(act[sl2]).to(dev))
+        pf, rf, _, tf, infos_f = full2.step(torch.from_numpy(act).to(dev))
+        assert np.array_equal(np.asarray(ps), np.asarray(pf)[sl2]), f"native step {step}: populations differ"
+        assert torch.equal(infos_s["GEBV"], infos_f["GEBV"][sl2]), f"native step {step}: GEBV differs"
+        assert rs.shape == (total2,) and torch.equal(rs, rf), f"native step {step}: gathered rewards differ"
+        assert np.array_equal(ts, tf)
+    dist.barrier()
+    if rank == 0:
+        print(f"native all-gather ok: {world} ranks, {total2} envs, bg_allgather_f32 == unsharded rewards on every rank")
     dist.barrier()
     if rank == 0:
         print(f"multi-gpu check ok: {world} ranks, {total} envs, sharded == unsharded bit for bit")

@@ -502,3 +502,32 @@ def test_vec_device_mode_ring_autoreset_matches_oracle(cuda_device):
                 okey, opops, _ = cr.vec_reset(germ, n, num_envs, okey, "legacy")
                 assert np.allclose(env.reset_infos["GEBV"].cpu().numpy(), cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)
             assert np.array_equal(np.asarray(pop), opops)
+
+
+def test_reference_parent_gather_idiom_on_packed_populations(cuda_device):
+    """`populations[arange_envs, actions]` (breedgym/vector/vec_env.py:89-90): a lazy per-env parents view whose
+    materialisation equals numpy fancy indexing and whose cross equals `env.cross(actions)`; other tuple indices are
+    plain numpy multi-axis indexing (not parent pairs)."""
+    from breedgym_b200.population import ParentsView
+
+    E, n = 3, 20
+    env = gym().make("VecBreedGym", num_envs=E, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n)
+    pops, _ = env.reset(seed=4)
+    host = np.asarray(pops)
+    rng = np.random.default_rng(0)
+    actions = rng.integers(0, n, (E, 7, 2))
+    arange_envs = np.arange(E)[:, None, None]
+    parents = pops[arange_envs, actions]
+    assert isinstance(parents, ParentsView) and parents.shape == (E, 7, 2, 1000, 2)
+    assert np.array_equal(np.asarray(parents), host[arange_envs, actions])
+    env.simulator.set_seed(5)
+    a = np.asarray(env.cross(parents))
+    env.simulator.set_seed(5)
+    b = np.asarray(env.cross(actions))
+    assert a.shape == (E, 7, 1000, 2) and np.array_equal(a, b)
+    # a homogeneous tuple of index arrays is numpy multi-axis indexing, not a parents view
+    rows, cols = np.array([0, 2]), np.array([1, 3])
+    assert np.array_equal(pops[(rows, cols)], host[(rows, cols)])
+    assert np.array_equal(pops[1, 2:4], host[1, 2:4])
+    single = pops[0]
+    assert np.array_equal(np.asarray(single[[3, 1, 2]]), host[0][[3, 1, 2]])

@@ -218,6 +218,14 @@ def test_double_haploid_bit_exact(cuda_device, layout):
     assert np.array_equal(np.asarray(got)[..., 0], np.asarray(got)[..., 1])  # homozygous lines
     one = sim.double_haploid(pop, n_offspring=1)
     assert one.shape == (6, m, 2) and np.array_equal(np.asarray(one), osim.double_haploid(pop, 1))
+    # a batch of populations = vmap(double_haploid, in_axes=(None, 0)): ONE key for every env, one launch
+    pops = rng.random((3, 5, m, 2)) < 0.5
+    sim.set_seed(8)
+    batch = np.asarray(sim.double_haploid(pops, n_offspring=2))
+    assert batch.shape == (3, 5, 2, m, 2)
+    for e in range(3):
+        osim.set_seed(8)
+        assert np.array_equal(batch[e], osim.double_haploid(pops[e], 2))
 
 
 def test_double_haploid_matches_golden(cuda_device, golden):
@@ -237,7 +245,7 @@ def test_double_haploid_matches_golden(cuda_device, golden):
         pop = sim.as_packed(g["pop"])
         out = sim._empty_words(len(pop), 3)
         key = np.ascontiguousarray(g["key"], dtype=np.uint32)
-        _lib.check(_lib.load().bg_double_haploid(sim._engine, pop.words.data_ptr(), out.data_ptr(), len(pop), 3,
+        _lib.check(_lib.load().bg_double_haploid(sim._engine, pop.words.data_ptr(), out.data_ptr(), 1, len(pop), 3,
                                                  _lib.nptr(key), sim._layout(), sim._schedule(), sim._stream()))
         torch.cuda.synchronize()
         from breedgym_b200.population import PackedPopulation

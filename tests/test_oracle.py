@@ -5,8 +5,12 @@ inputs come from `chromax.sample_data`, absent); what exists: the Random123
 Threefry vectors, the values JAX documents for key(0), and this repo's committed
 self-pins (tests/golden).
 """
+from pathlib import Path
+
 import numpy as np
 import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
 
 from oracle import c_oracle as co
 from oracle import chromax_ref as cr
@@ -145,3 +149,35 @@ def test_recombination_vector_from_map_files():
     rw = cr.recombination_vector(wheat)
     assert len(cr.chr_lens(wheat)) == 21 and rw.max() <= 0.5 and rw.min() >= 0.0
     assert len(cr.trait_columns(wheat)) == 7
+
+
+def test_chromax_pins():
+    """Genotype-level fixtures produced by REAL jax + chromax (scripts/pin_with_chromax.py).  Not producible on the build
+    image (neither package is installable), so this skips until tests/golden/chromax_pins.npz is committed; from then on
+    it pins the oracle -- PRNG layout, key schedule, Haldane conversion, constructor key split, select order -- to the
+    real implementation with the package defaults (rng_layout="legacy", key_schedule="S2")."""
+    import pandas as pd
+
+    pins = ROOT / "tests" / "golden" / "chromax_pins.npz"
+    if not pins.exists():
+        pytest.skip("tests/golden/chromax_pins.npz not generated yet (needs real jax + chromax: scripts/pin_with_chromax.py)")
+    g = dict(np.load(pins))
+    layout = "partitionable" if bool(g["threefry_partitionable"]) else "legacy"
+    data = ROOT / "breedgym_b200" / "data"
+    germ = np.load(data / "sample_geno.npy")
+    assert np.array_equal(jp.split(jp.key(99), 5, layout), g["split5"])
+    assert np.array_equal(jp.random_bits(jp.key(99), 9, layout), g["bits9"])
+    assert np.array_equal(jp.permutation(jp.key(11), 2000, layout), g["perm2000"])
+    r = cr.recombination_vector(pd.read_table(data / "sample_with_r_genetic_map.txt", sep="\t"))
+    assert np.array_equal(r, g["recombination_vec_r"])
+    assert np.array_equal(cr.recombination_vector(pd.read_table(data / "sample_genetic_map.txt", sep="\t")), g["recombination_vec_cm"])
+    assert np.array_equal(cr.cross(germ[g["pairs"]], r, jp.key(42), 0.0, "S2", layout), g["functional_cross_key42"])
+    eff = cr.marker_effects(pd.read_table(data / "sample_with_r_genetic_map.txt", sep="\t"), ["Yield"])
+    osim = cr.OracleSimulator(r, eff, seed=7, layout=layout)
+    # chromax draws its GxE effects at construction: one split of key(seed) (breedgym_b200/simulator.py does the same)
+    assert np.array_equal(jp.split(jp.key(7), 2, layout)[0], g["random_key_after_init_seed7"])
+    osim.set_seed(3)
+    assert np.array_equal(osim.cross(germ[g["pairs"]]), g["cross_seed3"])
+    assert np.array_equal(osim.cross(germ[g["pairs"]]), g["cross_seed3_second_call"])
+    _, _, idx = cr.vec_reset(np.zeros((50, 1, 2), bool), 20, 3, jp.key(7), layout)
+    assert np.array_equal(idx, g["reset_idx"])
