@@ -73,6 +73,7 @@ def config_dict(n_gpus, replicas=REPLICAS, envs_per_gpu=None, envs_total=None):
               f"per-kernel breakdown: 256 MiB flush",
         "observation": "packed bit planes resident in HBM (bool observation materialised on request only)",
         "rng": "threefry2x32 legacy layout, key schedule S2, seed 7",
+        "stream": "steps on a CUDA stream of priority -1 (torch.cuda.Stream(priority=-1)); the library's mask lookahead runs on its own side stream at priority 0",
     }
 
 
@@ -357,7 +358,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     h = Harness(torch, dist, dev, world)
-    if args.stream_priority is not None:  # diagnostics: run everything on a stream of this priority
+    if args.stream_priority != 0:
+        # The step stream gets a higher priority than the library's side stream (which generates the crossover masks
+        # of the FOLLOWING steps, one launch per batch of steps): whenever an SM has room, the block scheduler then
+        # places the step kernel's CTAs first and the mask kernel only fills what is left (torch's default stream has
+        # the lowest priority there is, so the side stream cannot be put below it).
         torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=args.stream_priority))
 
     germ, gmap = workload_inputs()
@@ -597,7 +602,8 @@ def main():
     ap.add_argument("--no-legs", action="store_true", help="skip the C1 / C3 / C4 legs")
     ap.add_argument("--replicas", type=int, default=REPLICAS, help="independent workload copies stepped round-robin")
     ap.add_argument("--skip-e2e", action="store_true", help="diagnostics: only the device-resident value")
-    ap.add_argument("--stream-priority", type=int, default=None, help="diagnostics: run on a torch stream of this priority")
+    ap.add_argument("--stream-priority", type=int, default=-1,
+                    help="priority of the CUDA stream the steps run on (default -1: above the library's mask side stream; 0: torch's current stream)")
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU,
                     help="envs per GPU (default 64 = BASELINE config C2; 512 = one GPU's share of C5, 4096 envs on 8 GPUs)")
     args = ap.parse_args()

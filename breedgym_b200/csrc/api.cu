@@ -177,8 +177,8 @@ int bg_engine_create(int device, bg_engine **out)
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     // tuning switches: the environment is read HERE, once (BG_OPT_<NAME>); nothing on the step path calls getenv
-    static const char *const names[] = {"fuse", "gebv_algo", "lookahead", "mask_nt", "mask_big_ctas", "blend_env_chunk",
-                                        "copy_engine", "mapped_d2h_max", "tc_target_ctas", "timing", "gebv_digits"};
+    static const char *const names[] = {"fuse", "gebv_algo", "lookahead", "mask_nt", "mask_big_ctas", "mask_ctas_per_sm", "blend_env_chunk",
+                                        "copy_engine", "mapped_d2h_max", "tc_target_ctas", "timing", "gebv_digits", "gebv_shape"};
     for (const char *name : names) {
         std::string env = "BG_OPT_";
         for (const char *c = name; *c; ++c) env += (char)toupper(*c);
@@ -209,6 +209,10 @@ int bg_engine_set_option(bg_engine *eng, const char *name, int64_t value)
         BG_REQUIRE(value >= 32 && value <= 256, BG_EINVAL, "mask_nt must be 32..256");
         o.mask_nt = (int)value / 32 * 32;
     } else if (n == "mask_big_ctas") o.mask_big_ctas = value != 0;
+    else if (n == "mask_ctas_per_sm") {
+        BG_REQUIRE(value >= 0 && value <= 16, BG_EINVAL, "mask_ctas_per_sm must be 0..16");
+        o.mask_ctas_per_sm = (int)value;
+    }
     else if (n == "blend_env_chunk") {
         BG_REQUIRE(value >= 1, BG_EINVAL, "blend_env_chunk must be >= 1");
         o.blend_env_chunk = (int)value;
@@ -216,7 +220,10 @@ int bg_engine_set_option(bg_engine *eng, const char *name, int64_t value)
     else if (n == "mapped_d2h_max") o.mapped_d2h_max = value;
     else if (n == "tc_target_ctas") o.tc_target_ctas = value;
     else if (n == "timing") o.timing = value != 0;
-    else if (n == "gebv_digits") {
+    else if (n == "gebv_shape") {
+        BG_REQUIRE(value >= 0 && value <= 2, BG_EINVAL, "gebv_shape must be 0 (auto), 1 (short K) or 2 (long K)");
+        o.gebv_shape = (int)value;
+    } else if (n == "gebv_digits") {
         BG_REQUIRE(value == 0 || (value >= 4 && value <= 8), BG_EINVAL, "gebv_digits must be 0 (auto) or 4..8");
         BG_REQUIRE(eng->m == 0, BG_ESTATE, "gebv_digits must be set before bg_engine_set_map");
         o.gebv_digits = (int)value;
@@ -230,6 +237,8 @@ int bg_engine_set_option(bg_engine *eng, const char *name, int64_t value)
 static void free_map(bg_engine *e)
 {
     cudaFree(e->d_thr);
+    cudaFree(e->d_thr_cmp);
+    e->d_thr_cmp = nullptr;
     cudaFree(e->d_wfix);
     cudaFree(e->d_inv_scale);
     cudaFree(e->d_wdig);
@@ -286,6 +295,14 @@ int bg_engine_set_map(bg_engine *eng, const float *recomb, const float *effects,
     for (int64_t j = 0; j < n_markers; ++j) thr[j] = threshold_of(recomb[j]);
     BG_CUDA(cudaMalloc(&eng->d_thr, nthr * sizeof(uint32_t)));
     BG_CUDA(cudaMemcpy(eng->d_thr, thr.data(), nthr * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // (bits >> 9) < T  <=>  bits < T << 9 as long as T << 9 fits 32 bits, i.e. T < 2^23 (r < 1): the kernels' fast path
+    bool fits = true;
+    for (size_t j = 0; j < nthr; ++j) fits = fits && thr[j] < (1u << 23);
+    if (fits) {
+        for (size_t j = 0; j < nthr; ++j) thr[j] <<= 9;
+        BG_CUDA(cudaMalloc(&eng->d_thr_cmp, nthr * sizeof(uint32_t)));
+        BG_CUDA(cudaMemcpy(eng->d_thr_cmp, thr.data(), nthr * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
 
     if (n_traits > 0) {
         // Fixed point: w_fix = rint(w * 2^s), one scale s per trait.  Sums of w_fix are exact integers, so a GEBV does

@@ -43,11 +43,13 @@ struct bg_options {
     int lookahead = BG_BATCH_MAX;  // steps of masks generated ahead on the side stream (0: none)
     int mask_nt = 128;         // threads of the small mask CTAs that run beside the step kernel
     int mask_big_ctas = 0;     // diagnostics: full-size mask CTAs on the side stream
+    int mask_ctas_per_sm = 0;  // lookahead batches: 0 = one small CTA per row; k > 0 = persistent grid of k small CTAs per SM
     int blend_env_chunk = 8;
     int copy_engine = 0;       // 1: never use the mapped-memory copy kernels
     long long mapped_d2h_max = 32 * 1024;
     long long tc_target_ctas = 0;  // 0: default
     int timing = 0;
+    int gebv_shape = 0;        // tensor-core GEBV pipeline shape: 0 auto, 1 short-K <SPM 1, S 3>, 2 long-K <SPM 2, S 4>
     int gebv_digits = 0;       // 0: as many base-256 digits as the map needs; 8: always 8 (cross-checks)
 };
 
@@ -61,6 +63,7 @@ struct bg_engine {
     int32_t Wpad = 0;    // W rounded up to a multiple of 32 (128-byte rows)
     int32_t T = 0;       // traits
     uint32_t *d_thr = nullptr;        // [Wpad*32 + 32] recombination thresholds (zero padded)
+    uint32_t *d_thr_cmp = nullptr;    // thresholds << 9 for the one-compare fast path (NULL when some threshold is 2^23)
     uint32_t mut_thr = 0;             // mutation threshold (0 = off)
     long long *d_wfix = nullptr;      // [T][Wpad*32] fixed-point effects (zero padded)
     double *d_inv_scale = nullptr;    // [T] 2^-s_t
@@ -80,7 +83,7 @@ struct bg_engine {
     size_t acc_cap = 0;                 // elements
     unsigned long long *d_acc2[2] = {nullptr, nullptr};  // gebv_tc2: all-zero between launches (one set per stream)
     size_t acc2_cap[2] = {0, 0};
-    size_t tc2_optin[2] = {48 * 1024, 48 * 1024};  // dynamic smem already opted into (plain, fused kernel)
+    size_t tc2_optin[3] = {48 * 1024, 48 * 1024, 48 * 1024};  // dynamic smem already opted into (GEBV short-K, fused kernel, GEBV long-K)
 };
 
 void bg_set_error(const std::string &msg);

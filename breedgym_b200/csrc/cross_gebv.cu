@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
     // its row index in out_pop / gebv (XG_NOROW past the end)
     __shared__ uint32_t row_src[2 * TILE_M], row_msk[2 * TILE_M], row_out[TILE_M];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) XG_STAMP(15, 0);
     const uint32_t in_base = smem_u32(smem);
     const uint32_t mask_base = in_base + XG_R * XG_IN_BYTES;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
     if (warp < 4) {
         mbar_wait(smem_u32(&bars.done), 0);
         if (tid == 0) XG_STAMP(15, 2);
-        digits_epilogue(tmem_d, tid, warp, row0, fa.rows, T, acc, inv_scale, out, gridDim.y, D, row_out);
+        digits_epilogue(tmem_d, tid, warp, row0, fa.rows, T, acc, inv_scale, out, gridDim.y, D, row_out[tid] == XG_NOROW ? -1 : (int64_t)row_out[tid]);
     }
     if (tid == 0) XG_STAMP(15, 3);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -19,6 +19,8 @@
 //
 // Per CTA: 54 KB of shared memory and 128 TMEM columns for <= 4 traits => 4 CTAs (40 warps) per SM.
 #include <cuda.h>
+
+#include <algorithm>
 #include <string.h>
 
 #include "bg_internal.h"
@@ -30,39 +32,46 @@ namespace {
 
 constexpr int T2_M = TILE_M;
 constexpr int T2_KS = STEP_K;       // markers per step (4 words per plane, 32 TMEM columns of int8x4)
-#ifndef T2_S_VAL
-#define T2_S_VAL 3
-#endif
-constexpr int T2_S = T2_S_VAL;      // A (TMEM) / B (smem) stages
 #ifndef T2_R_VAL
 #define T2_R_VAL 4
 #endif
 constexpr int T2_R = T2_R_VAL;      // raw macro-tile ring
-#ifndef T2_SPM_VAL
-#define T2_SPM_VAL 1
-#endif
-constexpr int T2_SPM = T2_SPM_VAL;  // steps per raw macro tile (wider TMA rows measured slower at C2: 32.3 us at 2, 35.6 us at 4, 31.8 us at 1)
 constexpr int T2_THREADS = 256 + 64;
-constexpr uint32_t T2_RAW_ROW = 16 * T2_SPM;                 // bytes per plane-row in a macro tile
-constexpr uint32_t T2_RAW_BYTES = 2 * T2_M * T2_RAW_ROW;     // 256 plane-rows x 16 B
+// Two pipeline shapes, chosen per launch (measured at BASELINE C2 / C4, B200):
+//   <SPM 1, S 3>  one 128-marker step per TMA box (16-byte rows), 3 A/B stages: short K loops (C2: 30.7 us vs 35.5)
+//   <SPM 2, S 4>  two steps per box (32-byte rows: whole sectors), 4 stages: long K loops (C4: 0.86 ms vs 1.18)
+// SPM = steps per raw macro tile, S = A (TMEM) / B (smem) stages.
+#ifndef T2_LONG_SPM
+#define T2_LONG_SPM 2
+#endif
+#ifndef T2_LONG_S
+#define T2_LONG_S 4
+#endif
+constexpr int T2_LONG_K_STEPS = 256;  // steps per CTA from which the second shape is used
 
+template <int S>
 struct T2Bars {
     uint64_t raw_full[T2_R], raw_empty[T2_R];
-    uint64_t a_full[T2_S], a_empty[T2_S], b_full[T2_S];
+    uint64_t a_full[S], a_empty[S], b_full[S];
     uint64_t done;
 };
 
 // smem: raw ring [T2_R][256 plane-rows][16 B], then B stages [T2_S][N/8][8 ki][8][16 B]
+template <int SPM, int S>
 __global__ void __launch_bounds__(T2_THREADS, 4)
     gebv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, int64_t rows, const int8_t *__restrict__ bdig, int N, int T, int D,
                     int steps_total, int steps_per_split, unsigned long long *__restrict__ acc,
                     const double *__restrict__ inv_scale, float *__restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) T2Bars bars;
+    __shared__ __align__(8) T2Bars<S> bars;
+    constexpr uint32_t T2_RAW_ROW = 16 * SPM;              // bytes per plane-row in a macro tile
+    constexpr uint32_t T2_RAW_BYTES = 2 * T2_M * T2_RAW_ROW;  // 256 plane-rows
     __shared__ uint32_t tmem_base_slot;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: provably warp-uniform, so the MMA warp's loop lives on the uniform datapath
+    // (UTCIMMA back to back instead of an ELECT + R2UR sequence per instruction: ~70 -> ~10 cycles per MMA issued)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const uint32_t raw_base = smem_u32(smem);
     const uint32_t b_bytes = (uint32_t)N * T2_KS;
     const uint32_t b_base0 = raw_base + T2_R * T2_RAW_BYTES;
@@ -73,7 +82,7 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
     uint32_t tmem_cols = 32;
-    while (tmem_cols < d_cols + T2_S * (T2_KS / 4)) tmem_cols <<= 1;
+    while (tmem_cols < d_cols + S * (T2_KS / 4)) tmem_cols <<= 1;
 
     if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
@@ -84,9 +93,9 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
     if (tid == 0) {
         for (int i = 0; i < T2_R; ++i) {
             mbar_init(smem_u32(&bars.raw_full[i]), 1);            // expect_tx arrival of the TMA loader
-            mbar_init(smem_u32(&bars.raw_empty[i]), 4 * T2_SPM);  // 4 reader warps per step
+            mbar_init(smem_u32(&bars.raw_empty[i]), 4 * SPM);  // 4 reader warps per step
         }
-        for (int i = 0; i < T2_S; ++i) {
+        for (int i = 0; i < S; ++i) {
             mbar_init(smem_u32(&bars.a_full[i]), 4);   // the 4 warps of the group that filled the stage
             mbar_init(smem_u32(&bars.a_empty[i]), 1);  // tcgen05.commit
             mbar_init(smem_u32(&bars.b_full[i]), 1);   // expect_tx arrival of the loader
@@ -109,17 +118,21 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
         const int g = warp >> 2, r = tid & (T2_M - 1);
         const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quadrant
         for (int j = g; j < nst; j += 2) {
-            const int mt = j / T2_SPM, rs = mt % T2_R;
+            const int mt = j / SPM, rs = mt % T2_R;
             mbar_wait(smem_u32(&bars.raw_full[rs]), (mt / T2_R) & 1);
             // macro tile [row][plane][16 B x SPM]; this step's 16 B of each plane
-            const uint32_t src = raw_base + rs * T2_RAW_BYTES + (uint32_t)r * (2 * T2_RAW_ROW) + (uint32_t)(j % T2_SPM) * 16;
+            const uint32_t src = raw_base + rs * T2_RAW_BYTES + (uint32_t)r * (2 * T2_RAW_ROW) + (uint32_t)(j % SPM) * 16;
             const uint4 x0 = lds128(src), x1 = lds128(src + T2_RAW_ROW);
+            // cross-proxy WAR: these generic-proxy reads must be ordered before the async-proxy (TMA) write that refills
+            // the slot.  Without the fence the 32-byte-row shape returned wrong sums in half of the runs at 1 M markers
+            // (rows of the tile's first warp read the NEXT macro tile), the 16-byte-row shape in 1 of 24.
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[rs]));
             // the field arithmetic happens BEFORE waiting for the TMEM stage, so it hides the MMA's latency
             const DosageFields f = dosage_fields(x0, x1);
-            const int as = j % T2_S;
-            if (j >= T2_S) mbar_wait(smem_u32(&bars.a_empty[as]), ((j / T2_S) - 1) & 1);  // MMAs of the previous use retired
+            const int as = j % S;
+            if (j >= S) mbar_wait(smem_u32(&bars.a_empty[as]), ((j / S) - 1) & 1);  // MMAs of the previous use retired
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             dosage_to_tmem(tmem_a + lane_sel + (uint32_t)as * (T2_KS / 4), f);
             __syncwarp();
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
         if (lane == 0) {
             // ---------------- raw bit-plane tiles (TMA 2-D) ----------------
             const int y = (int)(2 * row0);  // plane-row coordinate
-            const int nmt = (nst + T2_SPM - 1) / T2_SPM;
+            const int nmt = (nst + SPM - 1) / SPM;
             for (int mt = 0; mt < nmt; ++mt) {
                 const int rs = mt % T2_R;
                 if (mt >= T2_R) mbar_wait(smem_u32(&bars.raw_empty[rs]), ((mt / T2_R) - 1) & 1);
@@ -138,14 +151,14 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
                 asm volatile(
                     "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                         raw_base + rs * T2_RAW_BYTES),
-                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((s_begin + mt * T2_SPM) * 4), "r"(y), "r"(full)
+                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((s_begin + mt * SPM) * 4), "r"(y), "r"(full)
                     : "memory");
             }
         } else if (lane == 1) {
             // ---------------- digit tiles (1-D bulk copies) ----------------
             for (int j = 0; j < nst; ++j) {
-                const int bs = j % T2_S;
-                if (j >= T2_S) mbar_wait(smem_u32(&bars.a_empty[bs]), ((j / T2_S) - 1) & 1);
+                const int bs = j % S;
+                if (j >= S) mbar_wait(smem_u32(&bars.a_empty[bs]), ((j / S) - 1) & 1);
                 const uint32_t full = smem_u32(&bars.b_full[bs]);
                 mbar_arrive_expect_tx(full, b_bytes);
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -158,8 +171,8 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
         // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues ----------------
         const uint32_t idesc = idesc_u8s8(N);
         for (int j = 0; j < nst; ++j) {
-            const int as = j % T2_S;
-            const uint32_t par = (j / T2_S) & 1;
+            const int as = j % S;
+            const uint32_t par = (j / S) & 1;
             const uint32_t a_taddr = tmem_a + (uint32_t)as * (T2_KS / 4);
             const uint64_t bdesc = make_smem_desc(b_base0 + as * b_bytes, 128, 1024);
             mbar_wait(smem_u32(&bars.b_full[as]), par);
@@ -233,20 +246,25 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
     // 2-D view of the packed population: [2*rows plane-rows][Wpad words]; box = 4 words x 256 plane-rows
     const cuuint64_t gdim[2] = {(cuuint64_t)eng->Wpad, (cuuint64_t)(2 * rows)};
     const cuuint64_t gstride[1] = {(cuuint64_t)eng->Wpad * 4};
-    const cuuint32_t box[2] = {4 * T2_SPM, 2 * T2_M};
+    // steps one CTA would run with the short-K shape's split (4 CTAs per SM, >= 8 steps each)
+    int64_t ks = 4LL * eng->sm_count / std::max<int64_t>(tiles, 1);
+    ks = std::max<int64_t>(1, std::min<int64_t>(ks, (steps + 7) / 8));
+    const bool long_k = eng->opt.gebv_shape ? eng->opt.gebv_shape == 2 : steps / ks >= T2_LONG_K_STEPS;
+    const int SPM = long_k ? T2_LONG_SPM : 1, S = long_k ? T2_LONG_S : 3;
+    const cuuint32_t box[2] = {(cuuint32_t)(4 * SPM), 2 * T2_M};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t *>(pop), gdim, gstride, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BG_REQUIRE(cr == CUDA_SUCCESS, BG_ECUDA, "cuTensorMapEncodeTiled failed");
 
-    const size_t smem = (size_t)T2_R * T2_RAW_BYTES + (size_t)T2_S * N * T2_KS;
+    const size_t smem = (size_t)T2_R * (2 * T2_M * 16 * SPM) + (size_t)S * N * T2_KS;
     BG_REQUIRE(smem <= (size_t)eng->max_smem_optin, BG_ELIMIT, "too many traits for the tensor-core GEBV tile");
     // residency: TMEM columns (512 per SM) and shared memory
     uint32_t d_cols = 32;
     while ((int)d_cols < N) d_cols <<= 1;
     uint32_t tcols = 32;
-    while (tcols < d_cols + T2_S * (T2_KS / 4)) tcols <<= 1;
+    while (tcols < d_cols + S * (T2_KS / 4)) tcols <<= 1;
     int resident = (int)(512 / tcols);
     const int by_smem = (int)(227 * 1024 / (smem + 1024));
     if (by_smem < resident) resident = by_smem;
@@ -259,9 +277,11 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
     if (rc) return rc;
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
     // largest dynamic smem opted into so far, per engine (= per device: the attribute is per device)
-    if (smem > eng->tc2_optin[0]) {
-        BG_CUDA(cudaFuncSetAttribute(gebv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        eng->tc2_optin[0] = smem;
+    auto kern = long_k ? gebv_tc2_kernel<T2_LONG_SPM, T2_LONG_S> : gebv_tc2_kernel<1, 3>;
+    size_t &optin = long_k ? eng->tc2_optin[2] : eng->tc2_optin[0];
+    if (smem > optin) {
+        BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        optin = smem;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -277,7 +297,7 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
     const int8_t *bd = eng->d_wdig;
     const double *inv = eng->d_inv_scale;
     unsigned long long *acc = eng->d_acc2[scratch];
-    BG_CUDA(cudaLaunchKernelEx(&cfg, gebv_tc2_kernel, tmap, rows, bd, N, T, D, steps, sps, acc, inv, out));
+    BG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, rows, bd, N, T, D, steps, sps, acc, inv, out));
     BG_LAUNCHED();
     return BG_OK;
 }

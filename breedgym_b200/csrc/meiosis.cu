@@ -11,6 +11,8 @@
 // mask then either goes to global memory (vector env: masks are shared by all
 // envs, see blend_envs_kernel) or selects alleles from the two bit-plane rows of
 // the parent with 128-bit loads/stores (unique-key cross, double haploid).
+#include <algorithm>
+
 #include "bg_internal.h"
 #include "threefry.cuh"
 
@@ -20,11 +22,13 @@ constexpr int ILP = 4;
 constexpr uint32_t FULL = 0xffffffffu;
 
 struct RowParams {
-    const uint32_t *thr;
+    const uint32_t *thr;      // T[j] = clamp(ceil(r_j 2^23), 0, 2^23):  draw <=> (bits >> 9) < T
+    const uint32_t *thr_cmp;  // T[j] << 9 (NULL when some T = 2^23 would overflow): draw <=> bits < T << 9, one compare, no shift
     uint32_t mut_thr;
     uint32_t m, W, Wpad;
     uint32_t keys[BG_BATCH_MAX][2];  // mask mode: grid row g <-> gamete row g % rows of key g / rows (one launch per batch of keys)
     uint64_t rows;
+    uint64_t total_rows;  // rows x (keys | groups): the grid covers them one per CTA or in a strided loop
     uint32_t same_key;  // 1: every group of `rows` grid rows uses keys[0] (double haploids of E envs under ONE key)
     int schedule;
     int mode;
@@ -59,75 +63,124 @@ __device__ __forceinline__ void tf2x32_n(const TfKey &k, uint32_t (&x0)[N], uint
             x1[u] = __funnelshift_l(x1[u], x1[u], r) ^ x0[u];                          \
         }                                                                              \
     }
-#define BG_INJ(a, b, c)                          \
+#define BG_INJ(a, b)                             \
     _Pragma("unroll") for (int u = 0; u < N; ++u) \
     {                                            \
         x0[u] += (a);                            \
-        x1[u] += (b) + (c);                      \
+        x1[u] += (b);                            \
     }
-    BG_INJ(k.k0, k.k1, 0u)
-    BG_R(0, 13) BG_R(1, 15) BG_R(2, 26) BG_R(3, 6) BG_INJ(k.k1, k.k2, 1u)
-    BG_R(4, 17) BG_R(5, 29) BG_R(6, 16) BG_R(7, 24) BG_INJ(k.k2, k.k0, 2u)
-    BG_R(8, 13) BG_R(9, 15) BG_R(10, 26) BG_R(11, 6) BG_INJ(k.k0, k.k1, 3u)
-    BG_R(12, 17) BG_R(13, 29) BG_R(14, 16) BG_R(15, 24) BG_INJ(k.k1, k.k2, 4u)
-    BG_R(16, 13) BG_R(17, 15) BG_R(18, 26) BG_R(19, 6) BG_INJ(k.k2, k.k0, 5u)
+    // key-schedule words with the round counter folded in (uniform per row: computed once, not per block)
+    const uint32_t i1 = k.k2 + 1u, i2 = k.k0 + 2u, i3 = k.k1 + 3u, i4 = k.k2 + 4u, i5 = k.k0 + 5u;
+    BG_INJ(k.k0, k.k1)
+    BG_R(0, 13) BG_R(1, 15) BG_R(2, 26) BG_R(3, 6) BG_INJ(k.k1, i1)
+    BG_R(4, 17) BG_R(5, 29) BG_R(6, 16) BG_R(7, 24) BG_INJ(k.k2, i2)
+    BG_R(8, 13) BG_R(9, 15) BG_R(10, 26) BG_R(11, 6) BG_INJ(k.k0, i3)
+    BG_R(12, 17) BG_R(13, 29) BG_R(14, 16) BG_R(15, 24) BG_INJ(k.k1, i4)
+    BG_R(16, 13) BG_R(17, 15) BG_R(18, 26) BG_R(19, 6) BG_INJ(k.k2, i5)
 #undef BG_R
 #undef BG_INJ
 }
 
 // Draw the m Bernoulli bits `uniform(key)[j] < thr[j]` of one row into the zeroed
 // shared bit array S (marker j -> bit j&31 of S[j>>5]).
+// The integer (ALU) pipe bounds this loop: a Threefry block is 20 funnel shifts + 20 LOP3 there (the 35 additions go to
+// the FMA pipe as IMAD), so everything else on that pipe -- validity tests, selects, address arithmetic, the >> 9 of
+// the compare -- is overhead.  Groups of 32 counters whose draws are all inside the row take the FAST path: no
+// validity tests, thresholds preshifted (`bits < T << 9`), one uniform branch per ILP groups around the (rare)
+// recombination events; only the last, partial groups of a row go through the checked path.
 template <int LAYOUT, bool CONST_THR>
 __device__ __forceinline__ void draw_bits(uint32_t *S, const TfKey key, const uint32_t *__restrict__ thr,
-                                          uint32_t cthr, uint32_t m, uint32_t lane, uint32_t warp, uint32_t NW,
-                                          const uint32_t one)
+                                          const uint32_t *__restrict__ thr_cmp, uint32_t cthr, uint32_t m, uint32_t lane,
+                                          uint32_t warp, uint32_t NW, const uint32_t one)
 {
+    const bool fast_ok = CONST_THR ? (cthr < (1u << 23)) : (thr_cmp != nullptr);
+    const uint32_t ccmp = cthr << 9;
     if (LAYOUT == BG_LAYOUT_LEGACY) {
         // block c yields draw c (word 0) and draw c+h (word 1): two bit streams, the
         // second starting at bit offset h&31 of word h>>5.
         const uint32_t h = (m + 1) >> 1, G = (h + 31) >> 5, sh = h & 31, wsB = h >> 5;
+        const uint32_t Gfull = fast_ok ? ((m & 1) ? (h - 1) >> 5 : h >> 5) : 0u;  // groups with all 64 draws inside the row
         for (uint32_t g0 = warp * ILP; g0 < G; g0 += NW * ILP) {
-            uint32_t x0[ILP], x1[ILP], tA[ILP], tB[ILP];
+            uint32_t x0[ILP], x1[ILP], tA[ILP], tB[ILP], bA[ILP], bB[ILP];
+            if (g0 + ILP <= Gfull) {
+                const uint32_t c0 = g0 * 32 + lane;
 #pragma unroll
-            for (int u = 0; u < ILP; ++u) {
-                const uint32_t c = (g0 + u) * 32 + lane, cB = c + h;
-                const bool vA = c < h, vB = vA && cB < m;
-                x0[u] = c;
-                x1[u] = vB ? cB : 0u;  // odd m: the last block's second counter is the zero pad
-                tA[u] = vA ? (CONST_THR ? cthr : __ldg(thr + c)) : 0u;
-                tB[u] = vB ? (CONST_THR ? cthr : __ldg(thr + cB)) : 0u;
+                for (int u = 0; u < ILP; ++u) {
+                    x0[u] = c0 + 32 * u;
+                    x1[u] = c0 + 32 * u + h;
+                    tA[u] = CONST_THR ? ccmp : __ldg(thr_cmp + c0 + 32 * u);
+                    tB[u] = CONST_THR ? ccmp : __ldg(thr_cmp + c0 + 32 * u + h);
+                }
+                tf2x32_n<ILP>(key, x0, x1, one);
+                uint32_t any = 0;
+#pragma unroll
+                for (int u = 0; u < ILP; ++u) {
+                    bA[u] = __ballot_sync(FULL, x0[u] < tA[u]);
+                    bB[u] = __ballot_sync(FULL, x1[u] < tB[u]);
+                    any |= bA[u] | bB[u];
+                }
+                if (any == 0u) continue;  // recombination events are rare (r ~ 1e-3): most iterations end here
+            } else {
+#pragma unroll
+                for (int u = 0; u < ILP; ++u) {
+                    const uint32_t c = (g0 + u) * 32 + lane, cB = c + h;
+                    const bool vA = c < h, vB = vA && cB < m;
+                    x0[u] = c;
+                    x1[u] = vB ? cB : 0u;  // odd m: the last block's second counter is the zero pad
+                    tA[u] = vA ? (CONST_THR ? cthr : __ldg(thr + c)) : 0u;
+                    tB[u] = vB ? (CONST_THR ? cthr : __ldg(thr + cB)) : 0u;
+                }
+                tf2x32_n<ILP>(key, x0, x1, one);
+#pragma unroll
+                for (int u = 0; u < ILP; ++u) {
+                    bA[u] = __ballot_sync(FULL, (x0[u] >> 9) < tA[u]);
+                    bB[u] = __ballot_sync(FULL, (x1[u] >> 9) < tB[u]);
+                }
             }
-            tf2x32_n<ILP>(key, x0, x1, one);
 #pragma unroll
             for (int u = 0; u < ILP; ++u) {
                 const uint32_t g = g0 + u;
-                const uint32_t bA = __ballot_sync(FULL, (x0[u] >> 9) < tA[u]);
-                const uint32_t bB = __ballot_sync(FULL, (x1[u] >> 9) < tB[u]);
-                // recombination events are rare (r ~ 1e-3): one warp-uniform test skips the stitching for most groups
-                if ((bA | bB) != 0u && g < G) {
-                    if (lane == 0 && bA) atomicOr(&S[g], bA);
-                    if (lane == 1 && bB) atomicOr(&S[wsB + g], bB << sh);
-                    if (lane == 2 && sh && (bB >> (32 - sh))) atomicOr(&S[wsB + g + 1], bB >> (32 - sh));
+                if ((bA[u] | bB[u]) != 0u && g < G) {  // stitch the two streams (warp-uniform test)
+                    if (lane == 0 && bA[u]) atomicOr(&S[g], bA[u]);
+                    if (lane == 1 && bB[u]) atomicOr(&S[wsB + g], bB[u] << sh);
+                    if (lane == 2 && sh && (bB[u] >> (32 - sh))) atomicOr(&S[wsB + g + 1], bB[u] >> (32 - sh));
                 }
             }
         }
     } else {
         const uint32_t G = (m + 31) >> 5;
+        const uint32_t Gfull = fast_ok ? m >> 5 : 0u;
         for (uint32_t g0 = warp * ILP; g0 < G; g0 += NW * ILP) {
             uint32_t x0[ILP], x1[ILP], tA[ILP];
+            if (g0 + ILP <= Gfull) {
+                const uint32_t c0 = g0 * 32 + lane;
 #pragma unroll
-            for (int u = 0; u < ILP; ++u) {
-                const uint32_t c = (g0 + u) * 32 + lane;
-                x0[u] = 0u;
-                x1[u] = c;
-                tA[u] = (c < m) ? (CONST_THR ? cthr : __ldg(thr + c)) : 0u;
-            }
-            tf2x32_n<ILP>(key, x0, x1, one);
+                for (int u = 0; u < ILP; ++u) {
+                    x0[u] = 0u;
+                    x1[u] = c0 + 32 * u;
+                    tA[u] = CONST_THR ? ccmp : __ldg(thr_cmp + c0 + 32 * u);
+                }
+                tf2x32_n<ILP>(key, x0, x1, one);
 #pragma unroll
-            for (int u = 0; u < ILP; ++u) {
-                const uint32_t g = g0 + u;
-                const uint32_t b = __ballot_sync(FULL, ((x0[u] ^ x1[u]) >> 9) < tA[u]);
-                if (g < G && lane == 0) S[g] = b;
+                for (int u = 0; u < ILP; ++u) {
+                    const uint32_t b = __ballot_sync(FULL, (x0[u] ^ x1[u]) < tA[u]);
+                    if (lane == 0) S[g0 + u] = b;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < ILP; ++u) {
+                    const uint32_t c = (g0 + u) * 32 + lane;
+                    x0[u] = 0u;
+                    x1[u] = c;
+                    tA[u] = (c < m) ? (CONST_THR ? cthr : __ldg(thr + c)) : 0u;
+                }
+                tf2x32_n<ILP>(key, x0, x1, one);
+#pragma unroll
+                for (int u = 0; u < ILP; ++u) {
+                    const uint32_t g = g0 + u;
+                    const uint32_t b = __ballot_sync(FULL, ((x0[u] ^ x1[u]) >> 9) < tA[u]);
+                    if (g < G && lane == 0) S[g] = b;
+                }
             }
         }
     }
@@ -175,11 +228,12 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_ke
     uint32_t *S = smem;
     uint32_t *Mu = smem + (P.Wpad + 8);
     const uint32_t tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
-    const uint64_t grow = blockIdx.x;                  // row of the output arrays
-    const uint32_t kb = (uint32_t)(grow / P.rows);      // which key of the batch (0 unless mask mode)
-    const uint64_t q = grow - (uint64_t)kb * P.rows;   // gamete row of that key
     const bool has_mut = P.mut_thr != 0;
     const uint32_t W = P.W, Wpad = P.Wpad, m = P.m;
+    // one row per CTA, or (persistent launch, option mask_ctas_per_sm: fewer CTAs than rows) a strided loop over the rows
+    for (uint64_t grow = blockIdx.x; grow < P.total_rows; grow += gridDim.x) {  // row of the output arrays
+    const uint32_t kb = (uint32_t)(grow / P.rows);      // which key of the batch (0 unless mask mode)
+    const uint64_t q = grow - (uint64_t)kb * P.rows;   // gamete row of that key
 
     for (uint32_t i = tid; i < Wpad + 8; i += NT) {
         S[i] = 0;
@@ -196,8 +250,8 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_ke
     }
     __syncthreads();
 
-    draw_bits<LAYOUT, false>(S, krec, P.thr, 0u, m, lane, warp, NW, P.one);
-    if (has_mut) draw_bits<LAYOUT, true>(Mu, kmut, nullptr, P.mut_thr, m, lane, warp, NW, P.one);
+    draw_bits<LAYOUT, false>(S, krec, P.thr, P.thr_cmp, 0u, m, lane, warp, NW, P.one);
+    if (has_mut) draw_bits<LAYOUT, true>(Mu, kmut, nullptr, nullptr, P.mut_thr, m, lane, warp, NW, P.one);
     __syncthreads();
 
     // inclusive prefix-XOR over the whole row, in place: each warp owns a contiguous
@@ -238,7 +292,8 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_ke
             uint4 *uo = reinterpret_cast<uint4 *>(P.mut_out + grow * Wpad);
             for (uint32_t v = tid; v < W4; v += NT) uo[v] = Mu4[v];
         }
-        return;
+        __syncthreads();  // the row buffer is reused by the next row
+        continue;
     }
     int64_t src;
     uint4 *dst0, *dst1 = nullptr;
@@ -261,6 +316,8 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_ke
         dst0[v] = o;
         if (dst1) dst1[v] = o;
     }
+    __syncthreads();
+    }  // rows
 }
 
 // Vector env: out[e][q] = blend(pop[e][parents[e][q]] planes, mask[q]) for all envs e.
@@ -337,6 +394,7 @@ static int launch_rows(bg_engine *eng, int mode, int64_t rows, int nkeys, const 
                "n_markers too large for the shared-memory row buffer (limit ~1.8M markers, half with mutation)");
     RowParams P;
     P.thr = eng->d_thr;
+    P.thr_cmp = eng->d_thr_cmp;
     P.mut_thr = eng->mut_thr;
     P.m = (uint32_t)eng->m;
     P.W = (uint32_t)eng->W;
@@ -346,6 +404,7 @@ static int launch_rows(bg_engine *eng, int mode, int64_t rows, int nkeys, const 
         P.keys[b][1] = b < nkeys ? keys[b][1] : 0u;
     }
     P.rows = (uint64_t)rows;
+    P.total_rows = (uint64_t)(rows * grid_groups);
     P.same_key = groups > 0 ? 1u : 0u;
     P.schedule = schedule;
     P.mode = mode;
@@ -365,7 +424,10 @@ static int launch_rows(bg_engine *eng, int mode, int64_t rows, int nkeys, const 
     else
         kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 1024> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 1024>;
     if (smem > 48 * 1024) BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)(rows * grid_groups), NT, smem, st>>>(P);
+    // small_ctas (lookahead batches beside the step kernel): a persistent grid of mask_ctas_per_sm small CTAs per SM
+    int64_t grid = rows * grid_groups;
+    if (small_ctas && NT <= 256 && eng->opt.mask_ctas_per_sm > 0) grid = std::min<int64_t>(grid, (int64_t)eng->opt.mask_ctas_per_sm * eng->sm_count);
+    kern<<<(unsigned)grid, NT, smem, st>>>(P);
     BG_LAUNCHED();
     return BG_OK;
 }

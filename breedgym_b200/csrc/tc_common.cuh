@@ -164,11 +164,11 @@ constexpr int KSPLIT_MAX = 255;
 __device__ __forceinline__ void digits_epilogue(uint32_t tmem_d, int tid, int warp, int64_t row0, int64_t rows, int T,
                                                 unsigned long long *__restrict__ acc, const double *__restrict__ inv_scale,
                                                 float *__restrict__ out, unsigned nsplit, int D,
-                                                const uint32_t *out_row_map = nullptr)
+                                                int64_t out_row = -2)
 {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t row = row0 + tid;  // accumulator slot; the result goes to row `orow` of `out`
-    const int64_t orow = out_row_map ? (int64_t)out_row_map[tid] : row;
+    const int64_t row = row0 + tid;  // accumulator slot; the result goes to row `orow` of `out` (-2: the same row)
+    const int64_t orow = out_row == -2 ? row : out_row;
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
     for (int t = 0; t < T; ++t) {
         uint32_t v[8];

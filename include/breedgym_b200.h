@@ -86,7 +86,10 @@ int bg_engine_destroy(bg_engine *eng);
  *   gebv_algo (0)       default algorithm of bg_gebv, see bg_gebv_algo
  *   gebv_digits (0)     base-256 digits of the tensor-core GEBV operand: 0 = as many as the map needs,
  *                       4..8 fixed (set BEFORE bg_engine_set_map)
+ *   gebv_shape (0)      pipeline shape of the tensor-core GEBV: 0 = by K-loop length, 1 = short K, 2 = long K
  *   lookahead (8)       steps of crossover masks generated ahead of bg_vec_step on a side stream
+ *   mask_ctas_per_sm (0) k > 0: the lookahead mask kernel runs as a persistent grid of k small CTAs per SM (a fixed
+ *                       footprint beside the step kernel; measured slower than one CTA per row on a lower-priority stream)
  *   mask_nt (128), mask_big_ctas (0), blend_env_chunk (8), tc_target_ctas (0 = auto),
  *   copy_engine (0), mapped_d2h_max (32768), timing (0)      launch-shape / transfer tuning */
 int bg_engine_set_option(bg_engine *eng, const char *name, int64_t value);

@@ -31,7 +31,7 @@ def main():
             sys.stderr.write(out)
             raise SystemExit(f"nvcc failed for {obj.name}")
     so = out_dir / (name + ".so")
-    subprocess.check_call([B._nvcc(), "-shared", "-o", str(so), *[str(o) for o, _ in procs], "-gencode", "arch=compute_100a,code=sm_100a"])
+    subprocess.check_call([B._nvcc(), "-shared", "-o", str(so), *[str(o) for o, _ in procs], "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     print(so)
 
 

@@ -4,10 +4,10 @@
 //
 // Every thread runs CHAINS independent dependency chains of one instruction kind, 8192 deep, at full occupancy
 // (2048 threads per SM); ops/s = threads x chains x depth x ops per link / time, best of 5.  Kinds:
-//   iadd    x += y                      (IADD3, ALU pipe)
+//   iadd    x += y; y += x              (IADD3)
 //   lop3    x = (x ^ y) & z | w-ish     (LOP3, ALU pipe)
 //   shf     x = funnelshift(x, x, r)    (SHF, ALU pipe)
-//   imad    x = y * one + x             (IMAD, FMA pipe: `one` is a kernel argument, so it is not folded to IADD3)
+//   imad    x = y * one + x; y = x * one + y   (IMAD, FMA pipe: `one` is a kernel argument, so it is not folded to IADD3)
 //   tf_alu  the Threefry round with the add as IADD3:  x0 += x1; x1 = rotl(x1, r) ^ x0        (3 ops, all ALU)
 //   tf_mix  the Threefry round as meiosis.cu issues it: x0 = x1 * one + x0 (IMAD) ; SHF ; LOP3 (3 ops, two pipes)
 // Output: one JSON object; `int32_gops` = the tf_mix rate (the most the rounds of a Threefry block can issue at),
@@ -35,10 +35,16 @@ __global__ void __launch_bounds__(1024, 2) probe(unsigned *out, unsigned one, un
         for (int u = 0; u < 8; ++u) {
 #pragma unroll
             for (int c = 0; c < CHAINS; ++c) {
-                if (KIND == 0) x0[c] += x1[c];
+                if (KIND == 0) {  // two dependent adds per link (a lone x0 += x1 with constant x1 folds into one multiply-add)
+                    x0[c] += x1[c];
+                    x1[c] += x0[c];
+                }
                 if (KIND == 1) x0[c] = (x0[c] ^ x1[c]) | (x0[c] & seed);
                 if (KIND == 2) x0[c] = __funnelshift_l(x0[c], x0[c], 13);
-                if (KIND == 3) x0[c] = x1[c] * one + x0[c];
+                if (KIND == 3) {
+                    x0[c] = x1[c] * one + x0[c];
+                    x1[c] = x0[c] * one + x1[c];
+                }
                 if (KIND == 4) {
                     x0[c] += x1[c];
                     x1[c] = __funnelshift_l(x1[c], x1[c], 13 + u) ^ x0[c];
@@ -60,7 +66,7 @@ template <int KIND, int CHAINS>
 double run(int sms, unsigned *d_out)
 {
     const int blocks = sms * 2 * 4;
-    const double ops_per_link = KIND >= 4 ? 3.0 : 1.0;
+    const double ops_per_link = KIND >= 4 ? 3.0 : ((KIND == 0 || KIND == 3) ? 2.0 : 1.0);
     float best = 1e30f;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
