@@ -375,7 +375,7 @@ def run_ours(args):
     def env_factory(total_envs):
         def make_env(info_device):
             if world > 1:  # one process per GPU, env-sharded; the reward all-gather goes through bg_allgather_f32
-                env = ShardedVecBreedGym(total_envs=total_envs, info_device=info_device, **env_kw)
+                env = ShardedVecBreedGym(total_envs=total_envs, info_device=info_device, async_rewards=True, **env_kw)
             else:
                 env = VecBreedGym(num_envs=total_envs, info_device=info_device, **env_kw)
             env.reset(seed=7)

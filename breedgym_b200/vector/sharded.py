@@ -53,9 +53,15 @@ def allgather_rewards(local: torch.Tensor, counts: Sequence[int], group=None) ->
 
 
 class RewardGather:
-    """The path's one collective through the C ABI (`bg_allgather_f32`: ncclAllGather on the step's own stream, no
-    host round trip; the communicator is created and warmed once).  `torch.distributed` is used only to hand NCCL's
-    unique id to the other ranks.  Equal shard sizes only (the sharded env pads otherwise through torch)."""
+    """The path's one collective through the C ABI (`bg_allgather_f32`: ncclAllGather, no host round trip; the
+    communicator is created and warmed once).  `torch.distributed` is used only to hand NCCL's unique id to the other
+    ranks.  Equal shard sizes only (the sharded env pads otherwise through torch).
+
+    The collective runs on its OWN stream: it waits (event) for the step that produced the local rewards, copies them
+    into a private staging buffer and all-gathers from there, so the step stream never waits for the slowest rank --
+    only whoever consumes the gathered rewards does.  `__call__(local, wait=True)` makes the step stream wait for the
+    result right away (plain in-order semantics); `wait=False` leaves that to the caller (`self.done` is the event).
+    """
 
     def __init__(self, simulator, world: int, rank: int, count: int, group=None):
         lib = _lib.load()
@@ -71,18 +77,30 @@ class RewardGather:
         self._destroy = lib.bg_comm_destroy
         self.world, self.count = world, count
         self.device = simulator.device
-        self._stream = simulator._stream
-        # two receive buffers, alternating: the rewards of an episode stay valid while the next episode runs
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._stream_ptr = ctypes.c_void_p(self.stream.cuda_stream)
+        self.ready = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        # two staging / receive buffers, alternating: the rewards of an episode stay valid while the next episode runs
+        self._stage = [torch.empty(count, dtype=torch.float32, device=self.device) for _ in range(2)]
         self._out = [torch.empty(world * count, dtype=torch.float32, device=self.device) for _ in range(2)]
-        self._out_ptr = [o.data_ptr() for o in self._out]
         self._pos = 0
 
-    def __call__(self, local: torch.Tensor) -> torch.Tensor:
+    def __call__(self, local: torch.Tensor, wait: bool = True) -> torch.Tensor:
         self._pos ^= 1
-        rc = self._fn(self._comm, local.data_ptr(), self._out_ptr[self._pos], self.count, self._stream())
+        stage, out = self._stage[self._pos], self._out[self._pos]
+        main = torch.cuda.current_stream(self.device)
+        self.ready.record(main)
+        self.stream.wait_event(self.ready)
+        with torch.cuda.stream(self.stream):
+            stage.copy_(local, non_blocking=True)  # the step's reward buffer is free again as soon as this has run
+        rc = self._fn(self._comm, stage.data_ptr(), out.data_ptr(), self.count, self._stream_ptr)
         if rc:
             _lib.check(rc)
-        return self._out[self._pos]
+        self.done.record(self.stream)
+        if wait:
+            main.wait_event(self.done)
+        return out
 
     def close(self):
         if self._comm:
@@ -101,11 +119,15 @@ class ShardedVecBreedGym:
 
     `step(actions)` takes THIS rank's actions `[count, n, 2]` and returns the local
     observation handle with the rewards of ALL envs.  `collective`: "native" = `bg_allgather_f32`
-    (NCCL through the C ABI, on the step's stream), "torch" = `torch.distributed` (gloo in the CPU
+    (NCCL through the C ABI, on its own stream), "torch" = `torch.distributed` (gloo in the CPU
     tests), "auto" = native when the group's backend is nccl and the shards are equal.
+    `async_rewards` (native collective, `info_device="device"`): the step stream does not wait for the
+    all-gather -- the following steps overlap it; wait for `env.rewards_done` (a CUDA event) before
+    reading the returned rewards on another stream, or call `env.wait_rewards()`.
     """
 
-    def __init__(self, total_envs: int, group=None, device: Optional[int] = None, collective: str = "auto", **kwargs):
+    def __init__(self, total_envs: int, group=None, device: Optional[int] = None, collective: str = "auto",
+                 async_rewards: bool = False, **kwargs):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -127,6 +149,16 @@ class ShardedVecBreedGym:
         self._gather = RewardGather(self.env.simulator, self.world, self.rank, self.count, group) \
             if (collective == "native" and self.world > 1) else None
         self._zeros = None
+        self.async_rewards = bool(async_rewards) and self._gather is not None
+
+    @property
+    def rewards_done(self):
+        return self._gather.done if self._gather is not None else None
+
+    def wait_rewards(self):
+        """Make the current stream wait for the last reward all-gather (no-op without the native collective)."""
+        if self._gather is not None:
+            torch.cuda.current_stream(self.env.device).wait_event(self._gather.done)
 
     def __getattr__(self, name):
         if name.startswith("_") or name == "env":
@@ -144,7 +176,7 @@ class ShardedVecBreedGym:
         if self.world == 1:
             return local
         if self._gather is not None:
-            return self._gather(local)
+            return self._gather(local, wait=not self.async_rewards)
         return allgather_rewards(local, self.counts, self.group)
 
     def step(self, local_actions):

@@ -48,7 +48,7 @@ def main():
     # equal shards: the reward all-gather goes through the C ABI (bg_allgather_f32 = ncclAllGather on the step's stream),
     # device-resident infos, observation ring; compared with the unsharded env on the same GPU
     total2 = 3 * world
-    shard2 = ShardedVecBreedGym(total_envs=total2, device=local, info_device="device", **kw)
+    shard2 = ShardedVecBreedGym(total_envs=total2, device=local, info_device="device", async_rewards=True, **kw)
     assert shard2.collective == "native", shard2.collective
     full2 = VecBreedGym(num_envs=total2, device=local, info_device="device", **kw)
     shard2.reset(seed=5)
@@ -59,6 +59,7 @@ def main():
         act = rng.integers(0, n, (total2, n, 2)).astype(np.int32)
         ps, rs, _, ts, infos_s = shard2.step(torch.from_numpy(act[sl2]).to(dev))
         pf, rf, _, tf, infos_f = full2.step(torch.from_numpy(act).to(dev))
+        shard2.wait_rewards()  # async_rewards: the all-gather ran on its own stream
         assert np.array_equal(np.asarray(ps), np.asarray(pf)[sl2]), f"native step {step}: populations differ"
         assert torch.equal(infos_s["GEBV"], infos_f["GEBV"][sl2]), f"native step {step}: GEBV differs"
         assert rs.shape == (total2,) and torch.equal(rs, rf), f"native step {step}: gathered rewards differ"
