@@ -51,6 +51,7 @@ _SIGNATURES = {
     "bg_gebv_digits": (c_int, [c_void_p]),
     "bg_reduce_max": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "bg_reduce_mean": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "bg_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "bg_reset_indices": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "bg_vec_reset": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]),

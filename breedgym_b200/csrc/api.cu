@@ -178,7 +178,7 @@ int bg_engine_create(int device, bg_engine **out)
     cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     // tuning switches: the environment is read HERE, once (BG_OPT_<NAME>); nothing on the step path calls getenv
     static const char *const names[] = {"fuse", "gebv_algo", "lookahead", "mask_nt", "mask_big_ctas", "mask_ctas_per_sm", "blend_env_chunk",
-                                        "copy_engine", "mapped_d2h_max", "tc_target_ctas", "timing", "gebv_digits", "gebv_shape"};
+                                        "copy_engine", "mapped_d2h_max", "tc_target_ctas", "timing", "gebv_digits", "gebv_shape", "rows_nt"};
     for (const char *name : names) {
         std::string env = "BG_OPT_";
         for (const char *c = name; *c; ++c) env += (char)toupper(*c);
@@ -220,7 +220,10 @@ int bg_engine_set_option(bg_engine *eng, const char *name, int64_t value)
     else if (n == "mapped_d2h_max") o.mapped_d2h_max = value;
     else if (n == "tc_target_ctas") o.tc_target_ctas = value;
     else if (n == "timing") o.timing = value != 0;
-    else if (n == "gebv_shape") {
+    else if (n == "rows_nt") {
+        BG_REQUIRE(value == 0 || (value >= 64 && value <= 1024 && value % 32 == 0), BG_EINVAL, "rows_nt must be 0 or a multiple of 32 in 64..1024");
+        o.rows_nt = (int)value;
+    } else if (n == "gebv_shape") {
         BG_REQUIRE(value >= 0 && value <= 2, BG_EINVAL, "gebv_shape must be 0 (auto), 1 (short K) or 2 (long K)");
         o.gebv_shape = (int)value;
     } else if (n == "gebv_digits") {
@@ -709,6 +712,13 @@ int bg_reduce_mean(bg_engine *eng, const float *gebv, int64_t E, int64_t per_env
     BG_ENTER(eng);
     BG_REQUIRE(E >= 0 && (E == 0 || (gebv && out)), BG_EINVAL, "bg_reduce_mean: bad argument");
     return bg_launch_reduce(gebv, E, per_env, out, 1, (cudaStream_t)stream);
+}
+
+int bg_topk(bg_engine *eng, const float *scores, int64_t rows, int64_t len, int32_t k, float *vals_out, int32_t *idx_out, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(rows >= 0 && len >= 0 && (rows == 0 || (scores && vals_out && idx_out)), BG_EINVAL, "bg_topk: bad argument");
+    return bg_launch_topk(scores, rows, len, k, vals_out, idx_out, (cudaStream_t)stream);
 }
 
 int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_total, int64_t env_begin, int64_t E, int64_t n_germ,

@@ -42,6 +42,7 @@ struct bg_options {
     int gebv_algo = 0;         // 0 auto, 1..3 as bg_gebv_algo
     int lookahead = BG_BATCH_MAX;  // steps of masks generated ahead on the side stream (0: none)
     int mask_nt = 128;         // threads of the small mask CTAs that run beside the step kernel
+    int rows_nt = 0;           // threads per CTA of the unique-key cross / mask kernel (0: by row length; 128..1024)
     int mask_big_ctas = 0;     // diagnostics: full-size mask CTAs on the side stream
     int mask_ctas_per_sm = 0;  // lookahead batches: 0 = one small CTA per row; k > 0 = persistent grid of k small CTAs per SM
     int blend_env_chunk = 8;
@@ -135,6 +136,9 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
 bool bg_cross_gebv_fused_ok(const bg_engine *eng, int64_t E, int64_t n_src, int64_t n);
 int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
                                int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st);
+
+// topk.cu
+int bg_launch_topk(const float *scores, int64_t rows, int64_t len, int k, float *vals_out, int32_t *idx_out, cudaStream_t st);
 
 // layout.cu
 int bg_launch_copy_mapped(const void *src, void *dst, size_t bytes, cudaStream_t st);

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
         // ---------------- expanders: group g takes steps j with j % 2 == g ----------------
         const int g = warp >> 2, r = tid & (T2_M - 1);
         const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quadrant
+        int pending = -1;  // A stage whose stores are issued but not yet published to the MMA warp
         for (int j = g; j < nst; j += 2) {
             const int mt = j / SPM, rs = mt % T2_R;
             mbar_wait(smem_u32(&bars.raw_full[rs]), (mt / T2_R) & 1);
@@ -131,12 +132,23 @@ __global__ void __launch_bounds__(T2_THREADS, 4)
             if (lane == 0) mbar_arrive(smem_u32(&bars.raw_empty[rs]));
             // the field arithmetic happens BEFORE waiting for the TMEM stage, so it hides the MMA's latency
             const DosageFields f = dosage_fields(x0, x1);
+            // the stores of this group's PREVIOUS step have had a whole iteration to land: publish them now instead of
+            // stalling on tcgen05.wait::st right behind the stores (22 % of the kernel's stall samples at C4)
+            if (pending >= 0) {
+                tmem_st_publish();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[pending]));
+            }
             const int as = j % S;
             if (j >= S) mbar_wait(smem_u32(&bars.a_empty[as]), ((j / S) - 1) & 1);  // MMAs of the previous use retired
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            dosage_to_tmem(tmem_a + lane_sel + (uint32_t)as * (T2_KS / 4), f);
+            dosage_to_tmem_issue(tmem_a + lane_sel + (uint32_t)as * (T2_KS / 4), f);
+            pending = as;
+        }
+        if (pending >= 0) {
+            tmem_st_publish();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[as]));
+            if (lane == 0) mbar_arrive(smem_u32(&bars.a_full[pending]));
         }
     } else if (warp == 8) {
         if (lane == 0) {

@@ -221,7 +221,7 @@ __device__ __forceinline__ uint4 blend4(uint4 h0, uint4 h1, uint4 M)
 }
 
 template <int LAYOUT, int NT_MAX>
-__global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : 1) meiosis_rows_kernel(const RowParams P)
+__global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : (NT_MAX == 512 ? 2 : 1)) meiosis_rows_kernel(const RowParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t wtot[32];
@@ -417,10 +417,23 @@ static int launch_rows(bg_engine *eng, int mode, int64_t rows, int nkeys, const 
     P.out = out;
     P.one = 1u;
     // small_ctas: 128-thread CTAs (8192 registers) for mask kernels that run beside the fused step kernel, see cross_gebv.cu
-    const int NT = eng->W <= 1024 ? (small_ctas ? eng->opt.mask_nt : 256) : 1024;
+    // CTA size by row length: short rows 256 threads (4 CTAs per SM; 128 when all rows then fit in ONE wave of 8 per SM, or
+    // beside the step kernel), mid rows 512 (2 per SM: one CTA's prologue / scan / store phases overlap the other's draw
+    // phase), long rows 1024
+    const int64_t total_rows = rows * (groups > 0 ? groups : nkeys);
+    int NT;
+    if (eng->W <= 1024) {
+        NT = small_ctas ? eng->opt.mask_nt : 256;
+        if (!small_ctas && total_rows > 4LL * eng->sm_count && total_rows <= 8LL * eng->sm_count) NT = 128;
+    } else {
+        NT = eng->W <= 8192 ? 512 : 1024;
+    }
+    if (eng->opt.rows_nt > 0 && !small_ctas) NT = eng->opt.rows_nt;
     void (*kern)(RowParams);
     if (NT <= 256)
         kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 256> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 256>;
+    else if (NT <= 512)
+        kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 512> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 512>;
     else
         kern = layout == BG_LAYOUT_LEGACY ? meiosis_rows_kernel<BG_LAYOUT_LEGACY, 1024> : meiosis_rows_kernel<BG_LAYOUT_PARTITIONABLE, 1024>;
     if (smem > 48 * 1024) BG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

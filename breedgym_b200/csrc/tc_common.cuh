@@ -107,7 +107,8 @@ __device__ __forceinline__ DosageFields dosage_fields(const uint4 x0, const uint
 // sit in their bytes: column q, byte b <-> K index 4q + b <-> marker 8b + q of the word, as the UNSIGNED byte
 // dosage * 4^(q/2); the digit table carries the inverse scale (api.cu), so all sums are exactly 64x.
 // 16 integer ops per 32 markers in total.
-__device__ __forceinline__ void dosage_to_tmem(uint32_t taddr, const DosageFields &f)
+// issue only: the stores are asynchronous; tmem_st_publish() makes them visible to the MMA warp's barrier round
+__device__ __forceinline__ void dosage_to_tmem_issue(uint32_t taddr, const DosageFields &f)
 {
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
@@ -116,8 +117,16 @@ __device__ __forceinline__ void dosage_to_tmem(uint32_t taddr, const DosageField
         for (int q = 0; q < 8; ++q) o[q] = ((q & 1) ? f.zo[jj] : f.ze[jj]) & (0x03030303u << (q & ~1));
         tmem_st8(taddr + 8 * jj, o);
     }
+}
+__device__ __forceinline__ void tmem_st_publish()
+{
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void dosage_to_tmem(uint32_t taddr, const DosageFields &f)
+{
+    dosage_to_tmem_issue(taddr, f);
+    tmem_st_publish();
 }
 
 __device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t a_taddr, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)

@@ -27,7 +27,7 @@ class WheatBreedGym(VectorWrapper):
         self.action_space = spaces.Box(-1e5, 1e5, shape=(self.num_envs, *action_shape))
 
     def _convert_actions(self, actions) -> torch.Tensor:
-        return _pairs_from_scores(actions, self.n_lines, self.device)
+        return _pairs_from_scores(actions, self.n_lines, self.device, self.simulator)
 
     def _index(self, pop: PackedPopulation) -> torch.Tensor:
         return self.simulator.GEBV_model(pop).sum(dim=-1)

@@ -67,6 +67,51 @@ class _ObsRing:
         return pos
 
 
+class _LazyInfos(dict):
+    """`reset_infos` of an AUTORESET in host mode: the GEBVs of the new populations are computed on the GPU in stream
+    order, but copied to the host only if somebody reads them (the step that triggered the autoreset returns the infos of
+    the final offspring, not these: vec_env.py:102-107) -- no extra copy + synchronisation inside that step."""
+
+    def __init__(self, fetch):
+        super().__init__()
+        self._fetch = fetch
+
+    def _materialise(self):
+        if self._fetch is not None:
+            fetch, self._fetch = self._fetch, None
+            super().__setitem__("GEBV", fetch())
+
+    def __getitem__(self, key):
+        self._materialise()
+        return super().__getitem__(key)
+
+    def __contains__(self, key):
+        return key == "GEBV" or super().__contains__(key)
+
+    def keys(self):
+        self._materialise()
+        return super().keys()
+
+    def items(self):
+        self._materialise()
+        return super().items()
+
+    def values(self):
+        self._materialise()
+        return super().values()
+
+    def get(self, key, default=None):
+        self._materialise()
+        return super().get(key, default)
+
+    def __iter__(self):
+        self._materialise()
+        return super().__iter__()
+
+    def __len__(self):
+        return 1 if self._fetch is not None else super().__len__()
+
+
 class VecBreedGym(VectorEnv):
     def __init__(
         self,
@@ -275,7 +320,7 @@ class VecBreedGym(VectorEnv):
         self.populations = self._own = out_pop
         self.step_idx += 1
         if done and self.autoreset:
-            self.reset()
+            self.reset(_auto=True)
         return self.populations, rews, np.zeros(E, dtype=bool), np.full(E, done), infos
 
     def _zero_rewards(self) -> torch.Tensor:
@@ -284,7 +329,7 @@ class VecBreedGym(VectorEnv):
             z = self._zeros = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
         return z  # shared read-only tensor: intermediate steps carry no reward
 
-    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None, _auto: bool = False):
         self.step_idx = 0
         if seed is not None:
             self.simulator.set_seed(seed)
@@ -321,7 +366,12 @@ class VecBreedGym(VectorEnv):
         else:
             words = sim._empty_words(E, n)
             pop, words_ptr = PackedPopulation._trusted(sim, words), words.data_ptr()
-        if host_info:
+        lazy = None
+        if host_info and _auto:
+            # autoreset inside a step: infos stay on the GPU (their own buffer) until somebody reads env.reset_infos
+            lazy = torch.empty((E, n, T), dtype=torch.float32, device=self.device)  # owned by the infos object
+            gebv_dev_ptr, gebv_host_ptr = lazy.data_ptr(), None
+        elif host_info:
             io = self._host_io((E, n, 2), T)
             gebv_dev_ptr, gebv_host_ptr = io["gebv_dev"], io["gebv_pin"]
         elif ring is not None:
@@ -336,7 +386,16 @@ class VecBreedGym(VectorEnv):
                                 self._raw_stream(self._dev_index))
         if rc:
             _lib.check(rc)
-        if host_info:
+        if lazy is not None:
+            done_ev = torch.cuda.Event()
+            done_ev.record(torch.cuda.current_stream(self.device))
+
+            def fetch(buf=lazy, ev=done_ev):
+                ev.synchronize()
+                return buf.cpu().numpy()
+
+            infos = _LazyInfos(fetch)
+        elif host_info:
             infos = {"GEBV": io["gebv_np"].copy()}
         elif ring is not None:
             infos = ring.infos[slot]

@@ -116,26 +116,34 @@ class SelectionScores(VectorWrapper):
         return super().step(low_level_actions)
 
 
-def _pairs_from_scores(scores, n_crosses: int, device) -> torch.Tensor:
+def _pairs_from_scores(scores, n_crosses: int, device, sim: Optional[Simulator] = None) -> torch.Tensor:
     """Pair scores `[E, n, n]` -> parent pairs `int32[E, n_crosses, 2]` on the GPU.
 
     Per env (breedgym/vector/vec_wrappers.py:100-112): the n_crosses best pairs (descending, ties -> lower flat
     index), offspring per pair = ceil(softmax(best values) * n_crosses), `jnp.repeat(..., total_repeat_length=n_crosses)`
-    (truncate, or pad with the last pair)."""
+    (truncate, or pad with the last pair).  The top-k over the E x n^2 scores is the library's radix-select kernel
+    (`bg_topk`) when a simulator is given; the torch formulation below it is the CPU cross-check."""
     s = torch.as_tensor(scores, dtype=torch.float32, device=device)
     E, n = s.shape[0], s.shape[-1]
     flat = s.reshape(E, -1) + 0.0  # -0.0 -> +0.0: the two compare equal, so they must get the same key
-    # top-n_crosses with jax.lax.top_k's order (descending, ties -> lower flat index) WITHOUT sorting all n^2 scores:
-    # 64-bit keys = (order-preserving integer image of the float32 score, inverted flat index) are unique, so a plain
-    # (unstable) top-k of the keys is that order exactly
-    bits = flat.view(torch.int32)
-    ordered = bits ^ ((bits >> 31) & 0x7FFFFFFF)  # monotone in the float value (sign-magnitude -> two's complement)
     L = flat.shape[1]  # scores are [E, a, n]: flat index -> (index // n, index % n)
-    low = (L - 1) - torch.arange(L, device=s.device, dtype=torch.int64)
-    keys = (ordered.to(torch.int64) << 32) + low
-    top = torch.topk(keys, n_crosses, dim=1, largest=True, sorted=True).values
-    idx = (L - 1) - (top & 0xFFFFFFFF)
-    vals = torch.gather(flat, 1, idx)
+    if sim is not None and flat.is_cuda and n_crosses <= 1024:
+        flat = flat.contiguous()
+        vals = torch.empty((E, n_crosses), dtype=torch.float32, device=flat.device)
+        idx32 = torch.empty((E, n_crosses), dtype=torch.int32, device=flat.device)
+        _lib.check(_lib.load().bg_topk(sim._engine, flat.data_ptr(), E, L, n_crosses, vals.data_ptr(), idx32.data_ptr(), sim._stream()))
+        idx = idx32.long()
+    else:
+        # top-n_crosses with jax.lax.top_k's order (descending, ties -> lower flat index) WITHOUT sorting all n^2 scores:
+        # 64-bit keys = (order-preserving integer image of the float32 score, inverted flat index) are unique, so a plain
+        # (unstable) top-k of the keys is that order exactly
+        bits = flat.view(torch.int32)
+        ordered = bits ^ ((bits >> 31) & 0x7FFFFFFF)  # monotone in the float value (sign-magnitude -> two's complement)
+        low = (L - 1) - torch.arange(L, device=s.device, dtype=torch.int64)
+        keys = (ordered.to(torch.int64) << 32) + low
+        top = torch.topk(keys, n_crosses, dim=1, largest=True, sorted=True).values
+        idx = (L - 1) - (top & 0xFFFFFFFF)
+        vals = torch.gather(flat, 1, idx)
     reps = torch.ceil(torch.softmax(vals, dim=1) * n_crosses).to(torch.int64)
     ends = torch.cumsum(reps, dim=1)  # pair b fills output slots [ends[b-1], ends[b])
     slots = torch.arange(n_crosses, device=s.device).expand(E, n_crosses).contiguous()
@@ -156,7 +164,7 @@ class PairScores(VectorWrapper):
         self.action_space = spaces.Box(-1e5, 1e5, shape=(self.num_envs, *action_shape))
 
     def _convert_actions(self, actions) -> torch.Tensor:
-        return _pairs_from_scores(actions, self.n_crosses, self.device)
+        return _pairs_from_scores(actions, self.n_crosses, self.device, self.simulator)
 
     def step(self, actions):
         low_level_actions = self._convert_actions(actions)

@@ -90,7 +90,7 @@ int bg_engine_destroy(bg_engine *eng);
  *   lookahead (8)       steps of crossover masks generated ahead of bg_vec_step on a side stream
  *   mask_ctas_per_sm (0) k > 0: the lookahead mask kernel runs as a persistent grid of k small CTAs per SM (a fixed
  *                       footprint beside the step kernel; measured slower than one CTA per row on a lower-priority stream)
- *   mask_nt (128), mask_big_ctas (0), blend_env_chunk (8), tc_target_ctas (0 = auto),
+ *   rows_nt (0 = by row length), mask_nt (128), mask_big_ctas (0), blend_env_chunk (8), tc_target_ctas (0 = auto),
  *   copy_engine (0), mapped_d2h_max (32768), timing (0)      launch-shape / transfer tuning */
 int bg_engine_set_option(bg_engine *eng, const char *name, int64_t value);
 /* recomb: host float32[m] (already shifted / chromosome starts = 0.5);
@@ -176,6 +176,14 @@ int bg_gebv_digits(bg_engine *eng);
 int bg_reduce_max(bg_engine *eng, const float *gebv, int64_t E, int64_t per_env, float *out, void *stream);
 /* np.mean(GEBV.to_numpy()) (breedgym/breedgym.py:153), accumulated in float64 */
 int bg_reduce_mean(bg_engine *eng, const float *gebv, int64_t E, int64_t per_env, float *out, void *stream);
+
+/* ---- top-k -------------------------------------------------------------------
+ * jax.lax.top_k along the last axis, as the action wrappers call it on flattened pair scores
+ * (breedgym/vector/vec_wrappers.py:101, breedgym/vector/breeding_programs_env.py:27): scores device float32
+ * [rows][len] -> the k largest per row, DESCENDING, ties -> lower index (-0.0 == +0.0); vals_out float32 [rows][k],
+ * idx_out int32 [rows][k].  k <= 1024.  Radix select + bitonic sort, one CTA per row. */
+int bg_topk(bg_engine *eng, const float *scores, int64_t rows, int64_t len, int32_t k, float *vals_out, int32_t *idx_out,
+            void *stream);
 
 /* ---- reset ------------------------------------------------------------------
  * VecBreedGym.reset's `_random_selection` (breedgym/vector/vec_env.py:22-27,

@@ -170,6 +170,10 @@ def test_vec_deterministic_trajectory_matches_oracle(cuda_device, layout):
             assert np.all(tru)
             assert np.allclose(rews, g.max(axis=(1, 2)), rtol=RTOL, atol=0)
             okey, opops, _ = cr.vec_reset(germ, n, num_envs, okey, layout)  # autoreset
+            if step == 9:  # the autoreset's infos are fetched lazily (host mode): read them once, leave them unread once
+                held = env.reset_infos
+                assert "GEBV" in held and np.allclose(held["GEBV"], cr.gebv(opops, osim.effects), rtol=RTOL, atol=0)
+                assert held["GEBV"].shape == (num_envs, n, 1) and list(held.keys()) == ["GEBV"]
         else:
             assert not np.any(tru) and np.all(rews == 0)
         assert np.array_equal(np.asarray(pop), opops)
@@ -531,3 +535,32 @@ def test_reference_parent_gather_idiom_on_packed_populations(cuda_device):
     assert np.array_equal(pops[1, 2:4], host[1, 2:4])
     single = pops[0]
     assert np.array_equal(np.asarray(single[[3, 1, 2]]), host[0][[3, 1, 2]])
+
+
+@pytest.mark.parametrize("rows,length,k", [(3, 144, 12), (5, 1000, 1), (2, 137, 137), (4, 136900, 370), (1, 70000, 1024)])
+def test_topk_kernel_matches_lax_top_k_semantics(cuda_device, rows, length, k):
+    """bg_topk (radix select + bitonic sort) == jax.lax.top_k: descending, ties -> lower index, -0.0 == +0.0; including
+    rows made of few distinct values (ties at the threshold) and an all-equal row."""
+    import torch
+
+    from breedgym_b200 import _lib
+    from breedgym_b200.simulator import Simulator
+
+    sim = Simulator(genetic_map=GMAP, device=0, seed=0)
+    rng = np.random.default_rng(rows * 7 + k)
+    x = rng.standard_normal((rows, length)).astype(np.float32)
+    x[0] = np.round(x[0] * 2) / 2          # heavy ties
+    if rows > 1:
+        x[1] = 0.0                          # all equal: the k lowest indices, in order
+        x[1, ::7] = -0.0
+    if rows > 2:
+        x[2, : length // 2] = -np.abs(x[2, : length // 2])  # negatives
+    xs = torch.from_numpy(x).to(cuda_device)
+    vals = torch.empty((rows, k), dtype=torch.float32, device=cuda_device)
+    idx = torch.empty((rows, k), dtype=torch.int32, device=cuda_device)
+    _lib.check(_lib.load().bg_topk(sim._engine, xs.data_ptr(), rows, length, k, vals.data_ptr(), idx.data_ptr(), sim._stream()))
+    torch.cuda.synchronize()
+    for r in range(rows):
+        rv, ri = jp.top_k(x[r] + np.float32(0.0), k)
+        assert np.array_equal(idx[r].cpu().numpy(), ri), f"row {r}: indices differ from lax.top_k"
+        assert np.array_equal(vals[r].cpu().numpy(), rv)
