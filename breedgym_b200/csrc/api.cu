@@ -268,6 +268,7 @@ int bg_engine_destroy(bg_engine *eng)
             if (b.freed) cudaEventDestroy(b.freed);
         }
         if (eng->tmp_event) cudaEventDestroy(eng->tmp_event);
+        if (eng->reset_ready) cudaEventDestroy(eng->reset_ready);
         cudaFree(eng->d_mut);
         cudaFree(eng->d_acc);
         for (int i = 0; i < 2; ++i) {
@@ -755,6 +756,36 @@ int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, cons
         BG_CUDA(cudaMemcpyAsync(gebv_host, gebv_dev, (size_t)E * n * eng->T * sizeof(float), cudaMemcpyDeviceToHost, st));
         BG_CUDA(cudaStreamSynchronize(st));
     }
+    return BG_OK;
+}
+
+int bg_vec_reset_prefetch(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, const uint32_t random_key[2], int64_t E_total,
+                          int64_t env_begin, int64_t E, int64_t n, int layout, int32_t *idx_dev, uint32_t *pop_out, float *gebv_dev,
+                          const float *germ_gebv, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(germ_gebv && gebv_dev, BG_EINVAL, "bg_vec_reset_prefetch: needs the germplasm's GEBVs (no GEBV kernel off the step stream)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!eng->side) BG_CUDA(cudaStreamCreateWithFlags(&eng->side, cudaStreamNonBlocking));
+    if (!eng->tmp_event) BG_CUDA(cudaEventCreateWithFlags(&eng->tmp_event, cudaEventDisableTiming));
+    if (!eng->reset_ready) BG_CUDA(cudaEventCreateWithFlags(&eng->reset_ready, cudaEventDisableTiming));
+    // behind everything enqueued so far on the caller's stream: the buffers' previous readers
+    BG_CUDA(cudaEventRecord(eng->tmp_event, st));
+    BG_CUDA(cudaStreamWaitEvent(eng->side, eng->tmp_event, 0));
+    const int rc = bg_vec_reset(eng, germplasm, n_germ, random_key, E_total, env_begin, E, n, layout, idx_dev, pop_out, gebv_dev, nullptr,
+                                germ_gebv, eng->side);
+    if (rc) return rc;
+    BG_CUDA(cudaEventRecord(eng->reset_ready, eng->side));
+    eng->reset_pending = true;
+    return BG_OK;
+}
+
+int bg_vec_reset_adopt(bg_engine *eng, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(eng->reset_pending, BG_ESTATE, "bg_vec_reset_adopt: no prefetched reset");
+    BG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, eng->reset_ready, 0));
+    eng->reset_pending = false;
     return BG_OK;
 }
 

@@ -78,6 +78,8 @@ struct bg_engine {
     unsigned long long use_clock = 0;
     cudaStream_t side = nullptr;        // lookahead stream
     cudaEvent_t tmp_event = nullptr;
+    cudaEvent_t reset_ready = nullptr;  // recorded behind a prefetched reset on the side stream
+    bool reset_pending = false;
     uint32_t *d_mut = nullptr;          // mutation scratch of bg_meiosis_masks
     size_t mut_cap = 0;                 // words
     unsigned long long *d_acc = nullptr;

@@ -246,6 +246,22 @@ class Simulator:
         _lib.check(_lib.load().bg_gebv(self._engine, w.data_ptr(), rows, out.data_ptr(), self._stream()))
         return out
 
+    def _top_k(self, values: torch.Tensor, k: int) -> torch.Tensor:
+        """`jax.lax.top_k(values, k)[1]` along the last axis on the GPU (descending, ties -> lower index): the library's
+        radix-select kernel (`bg_topk`); int64 indices `[..., k]`."""
+        v = values.to(device=self.device, dtype=torch.float32)
+        lead, length = tuple(v.shape[:-1]), v.shape[-1]
+        if k > 1024 or k > length:
+            if k > length:
+                raise ValueError(f"k={k} must not exceed the number of candidates {length}")
+            return torch.sort(v, dim=-1, descending=True, stable=True).indices[..., :k]
+        flat = v.reshape(-1, length).contiguous()
+        rows = flat.shape[0]
+        vals = torch.empty((rows, k), dtype=torch.float32, device=self.device)
+        idx = torch.empty((rows, k), dtype=torch.int32, device=self.device)
+        _lib.check(_lib.load().bg_topk(self._engine, flat.data_ptr(), rows, length, k, vals.data_ptr(), idx.data_ptr(), self._stream()))
+        return idx.long().reshape(*lead, k)
+
     # ---- chromax.Simulator surface -----------------------------------------------
     def set_seed(self, seed: int):
         self.random_key = _lib.key_data(seed)
@@ -381,12 +397,11 @@ class Simulator:
             values = self.GEBV_model(pop).sum(dim=-1)
         else:
             values = f_index(pop)
-        if isinstance(values, torch.Tensor):
-            values = values.detach().cpu().numpy()
-        values = np.asarray(values)
-        if values.ndim != 1:
+        if not isinstance(values, torch.Tensor):
+            values = torch.from_numpy(np.ascontiguousarray(np.asarray(values)))
+        if values.dim() != 1:
             raise ValueError("f_index must return one value per individual")
-        best = np.argsort(-values, kind="stable")[:k]
+        best = self._top_k(values, k).cpu().numpy()
         return self._gather(pop, best), best
 
     @staticmethod

@@ -43,10 +43,9 @@ class WheatBreedGym(VectorWrapper):
                                                      out.data_ptr(), G, n_src, k, n_src, sim._stream()))
         return out
 
-    @staticmethod
-    def _topk(values: torch.Tensor, k: int) -> torch.Tensor:
-        # descending, ties -> lower index (lax.top_k)
-        return torch.sort(values, dim=-1, descending=True, stable=True).indices[..., :k]
+    def _topk(self, values: torch.Tensor, k: int) -> torch.Tensor:
+        # descending, ties -> lower index (lax.top_k): the library's radix-select kernel
+        return self.simulator._top_k(values, k)
 
     def step(self, actions):
         env, sim = self.env, self.simulator

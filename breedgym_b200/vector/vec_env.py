@@ -124,6 +124,7 @@ class VecBreedGym(VectorEnv):
         info_device: str = "host",
         env_shard: Optional[Tuple[int, int]] = None,
         obs_ring: Optional[int] = None,
+        reset_prefetch: Optional[bool] = None,
         **kwargs,
     ):
         self.num_envs = num_envs
@@ -140,6 +141,9 @@ class VecBreedGym(VectorEnv):
         if obs_ring != 0 and obs_ring < 3:
             raise ValueError("obs_ring must be 0 (a fresh observation buffer per step) or >= 3")
         self.obs_ring = obs_ring
+        # device mode: the NEXT autoreset is drawn on the library's side stream while the episode runs (it depends on the
+        # reset key chain and the germplasm only) and adopted at the episode's end
+        self.reset_prefetch = (info_device == "device") if reset_prefetch is None else bool(reset_prefetch)
         self.simulator = Simulator(**kwargs)
         self.device = self.simulator.device
         # logical env range of this shard: envs [begin, begin + num_envs) of `total`
@@ -169,9 +173,12 @@ class VecBreedGym(VectorEnv):
         self._germ_words = None
         self._germ_gebv = None
         self.reuse_germplasm_gebv = True  # reset infos gathered from the germplasm's GEBVs (bit-identical to re-scoring)
+        self._pre = None           # prefetched reset: two buffer sets, alternating
         lib = _lib.load()
         self._vec_step_fn = lib.bg_vec_step
         self._vec_reset_fn = lib.bg_vec_reset
+        self._prefetch_fn = lib.bg_vec_reset_prefetch
+        self._adopt_fn = lib.bg_vec_reset_adopt
         self._raw_stream = torch._C._cuda_getCurrentRawStream
         self._dev_index = self.device.index
 
@@ -358,6 +365,22 @@ class VecBreedGym(VectorEnv):
         if idx is None or tuple(idx.shape) != (E, n):
             idx = self._idx_buf = torch.empty((E, n), dtype=torch.int32, device=self.device)
 
+        pre = self._pre
+        if (_auto and pre is not None and pre["pending"] and pre["n"] == n and pre["E"] == E
+                and pre["key"][0] == key[0] and pre["key"][1] == key[1]):
+            # this reset was drawn ahead of time on the side stream: the step stream waits for it and adopts its buffers
+            rc = self._adopt_fn(sim._engine, self._raw_stream(self._dev_index))
+            if rc:
+                _lib.check(rc)
+            pre["pending"] = False
+            words, gebv_t, idx = pre["bufs"][pre["slot"]]
+            self.random_key = _lib.key_split_at(self.random_key, 0, total + 1, sim.rng_layout)
+            self._reset_indices = idx
+            self.populations = self._own = PackedPopulation._trusted(sim, words)
+            self.reset_infos = {"GEBV": gebv_t}
+            self._prefetch_next(germ, germ_gebv_ptr, E, n, T)
+            return self.populations, self.reset_infos
+
         ring = self._obs_slots(n, T)
         if ring is not None:
             cur = self.populations
@@ -405,7 +428,27 @@ class VecBreedGym(VectorEnv):
         self._reset_indices = idx
         self.populations = self._own = pop
         self.reset_infos = infos
+        if self.reset_prefetch and self.autoreset and not host_info and germ_gebv_ptr is not None:
+            self._prefetch_next(germ, germ_gebv_ptr, E, n, T)
         return self.populations, self.reset_infos
+
+    def _prefetch_next(self, germ, germ_gebv_ptr, E, n, T):
+        """Draw the reset the NEXT autoreset will ask for (same `random_key`, same n) on the library's side stream."""
+        sim = self.simulator
+        begin, total = self.env_shard
+        pre = self._pre
+        if pre is None or pre["n"] != n or pre["E"] != E:
+            bufs = [(sim._empty_words(E, n), torch.empty((E, n, T), dtype=torch.float32, device=self.device),
+                     torch.empty((E, n), dtype=torch.int32, device=self.device)) for _ in range(2)]
+            pre = self._pre = {"n": n, "E": E, "bufs": bufs, "slot": 0, "pending": False, "key": None}
+        pre["slot"] ^= 1  # (the other set holds the populations adopted last: still the current episode's first parents)
+        words, gebv_t, idx = pre["bufs"][pre["slot"]]
+        key = np.array(self.random_key, dtype=np.uint32, copy=True)
+        rc = self._prefetch_fn(sim._engine, germ.data_ptr(), germ.shape[0], _lib.nptr(key), total, begin, E, n, sim._layout_id,
+                               idx.data_ptr(), words.data_ptr(), gebv_t.data_ptr(), germ_gebv_ptr, self._raw_stream(self._dev_index))
+        if rc:
+            _lib.check(rc)
+        pre["key"], pre["pending"] = key, True
 
     def get_info(self) -> dict:
         gebv = self.simulator.GEBV_model(self.populations)

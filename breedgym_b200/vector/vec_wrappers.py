@@ -86,7 +86,7 @@ class SelectionScores(VectorWrapper):
         E, n, k, nc = self.num_envs, self.individual_per_gen, self.k, self.n_crosses
         begin, total = self.env.env_shard
         s = torch.as_tensor(actions, device=dev).to(torch.float32).reshape(E, n)  # jax computes in float32 as well
-        best = torch.sort(s, dim=1, descending=True, stable=True).indices[:, :k]     # [E, k]
+        best = sim._top_k(s, k)                                                       # [E, k] (bg_topk: descending, ties -> lower index)
         tri = getattr(self, "_triu_dev", None)
         if tri is None or tri[0].device != dev:
             ia, ib = np.triu_indices(k, k=1)

@@ -204,6 +204,16 @@ int bg_vec_reset(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, cons
                  int64_t env_begin, int64_t E, int64_t n, int layout, int32_t *idx_dev, uint32_t *pop_out, float *gebv_dev,
                  float *gebv_host, const float *germ_gebv, void *stream);
 
+/* The NEXT autoreset, ahead of time: it depends on the reset key chain and the germplasm only
+ * (breedgym/vector/vec_env.py:109-130), so it can be drawn while the episode runs.  bg_vec_reset_prefetch enqueues the
+ * work of bg_vec_reset (germ_gebv required, no host copy) on the engine's internal side stream, behind everything
+ * enqueued so far on `stream` (the previous readers of the buffers); bg_vec_reset_adopt makes `stream` wait for it.
+ * The caller keeps pop_out / gebv_dev / idx_dev untouched in between. */
+int bg_vec_reset_prefetch(bg_engine *eng, const uint32_t *germplasm, int64_t n_germ, const uint32_t random_key[2],
+                          int64_t E_total, int64_t env_begin, int64_t E, int64_t n, int layout, int32_t *idx_dev,
+                          uint32_t *pop_out, float *gebv_dev, const float *germ_gebv, void *stream);
+int bg_vec_reset_adopt(bg_engine *eng, void *stream);
+
 /* ---- one-call vector-env step ------------------------------------------------
  * VecBreedGym.step hot path (breedgym/vector/vec_env.py:88-100) with host
  * buffers at the boundary: copies actions_host (int32 [E][n][2], pinned or
