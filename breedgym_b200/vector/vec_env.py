@@ -141,9 +141,9 @@ class VecBreedGym(VectorEnv):
         if obs_ring != 0 and obs_ring < 3:
             raise ValueError("obs_ring must be 0 (a fresh observation buffer per step) or >= 3")
         self.obs_ring = obs_ring
-        # device mode: the NEXT autoreset is drawn on the library's side stream while the episode runs (it depends on the
-        # reset key chain and the germplasm only) and adopted at the episode's end
-        self.reset_prefetch = (info_device == "device") if reset_prefetch is None else bool(reset_prefetch)
+        # the NEXT autoreset is drawn on the library's side stream while the episode runs (it depends on the reset key
+        # chain and the germplasm only) and adopted at the episode's end
+        self.reset_prefetch = True if reset_prefetch is None else bool(reset_prefetch)
         self.simulator = Simulator(**kwargs)
         self.device = self.simulator.device
         # logical env range of this shard: envs [begin, begin + num_envs) of `total`
@@ -366,7 +366,7 @@ class VecBreedGym(VectorEnv):
             idx = self._idx_buf = torch.empty((E, n), dtype=torch.int32, device=self.device)
 
         pre = self._pre
-        if (_auto and pre is not None and pre["pending"] and pre["n"] == n and pre["E"] == E
+        if (pre is not None and pre["pending"] and pre["n"] == n and pre["E"] == E
                 and pre["key"][0] == key[0] and pre["key"][1] == key[1]):
             # this reset was drawn ahead of time on the side stream: the step stream waits for it and adopts its buffers
             rc = self._adopt_fn(sim._engine, self._raw_stream(self._dev_index))
@@ -377,7 +377,19 @@ class VecBreedGym(VectorEnv):
             self.random_key = _lib.key_split_at(self.random_key, 0, total + 1, sim.rng_layout)
             self._reset_indices = idx
             self.populations = self._own = PackedPopulation._trusted(sim, words)
-            self.reset_infos = {"GEBV": gebv_t}
+            if host_info and not _auto:
+                self.reset_infos = {"GEBV": gebv_t.cpu().numpy()}
+            elif host_info:  # copied to the host only if somebody reads them (its own copy: the set is redrawn in two episodes)
+                owned, ev = gebv_t.clone(), torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+
+                def fetch(buf=owned, ev=ev):
+                    ev.synchronize()
+                    return buf.cpu().numpy()
+
+                self.reset_infos = _LazyInfos(fetch)
+            else:
+                self.reset_infos = {"GEBV": gebv_t}
             self._prefetch_next(germ, germ_gebv_ptr, E, n, T)
             return self.populations, self.reset_infos
 
@@ -428,7 +440,7 @@ class VecBreedGym(VectorEnv):
         self._reset_indices = idx
         self.populations = self._own = pop
         self.reset_infos = infos
-        if self.reset_prefetch and self.autoreset and not host_info and germ_gebv_ptr is not None:
+        if self.reset_prefetch and self.autoreset and germ_gebv_ptr is not None:
             self._prefetch_next(germ, germ_gebv_ptr, E, n, T)
         return self.populations, self.reset_infos
 
