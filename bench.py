@@ -297,9 +297,10 @@ class Harness:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(self, fn, steps):
+    def timed(self, fn, steps, finish=None):
         """`steps` calls bracketed by barrier + synchronize; returns (device seconds between two CUDA events, host
-        seconds spent enqueueing)."""
+        seconds spent enqueueing).  `finish` runs before the closing event (it orders the timed stream behind work
+        the steps started elsewhere: the reward exchange)."""
         # a full (generation 2) Python garbage collection walks every object the imported packages hold: 40-500 ms,
         # wherever it happens to fall.  Collect now and park the survivors so that none falls inside the timed region.
         gc.collect()
@@ -313,6 +314,8 @@ class Harness:
         for i in range(steps):
             fn(i)
         host = time.perf_counter() - t0
+        if finish is not None:
+            finish()
         end.record(stream)
         self.barrier()
         return start.elapsed_time(end) * 1e-3, host
@@ -328,13 +331,20 @@ def vec_value_leg(h, make_env, acts_dev, K, W, replicas, sample_clocks=None):
     def step(i):
         envs[i % replicas].step(acts_dev[i % n_act])
 
+    def finish():
+        # env-sharded runs exchange the rewards asynchronously (async_rewards): the closing event waits for every
+        # rank's rewards of every replica's last episode, so the timed region carries the whole exchange
+        for env in envs:
+            if hasattr(env, "wait_rewards"):
+                env.wait_rewards()
+
     h.spin_up()
     for i in range(max(W, replicas * (NUM_GENERATIONS + 1))):
         step(i)
-    h.timed(step, K)
+    h.timed(step, K, finish)
     if sample_clocks is not None:
         sample_clocks.start()
-    t_dev, t_host = h.timed(step, K)
+    t_dev, t_host = h.timed(step, K, finish)
     clocks = sample_clocks.stop() if sample_clocks is not None else None
     return envs, h.max_over_ranks(t_dev), t_host, clocks
 
@@ -396,6 +406,13 @@ def run_ours(args):
     launches0 = lib.bg_kernel_launches()
     envs, t_value, t_host, clocks = vec_value_leg(h, env_factory(total_envs), acts_dev, K, W, replicas, sampler)
     launches_total = lib.bg_kernel_launches() - launches0
+    reward_exchange = None
+    if world > 1:
+        how = envs[0].collective
+        reward_exchange = {"peer": "peer memory: the reward reduction stores into every rank's window over NVLink (bg_peer_*, no collective launch); "
+                                   "the closing event of the timed region waits for every rank's rewards",
+                           "native": "ncclAllGather through bg_allgather_f32 on its own stream",
+                           "torch": "torch.distributed all_gather"}[how]
     # launches inside the timed region: counted over one more pass of K steps
     l0 = lib.bg_kernel_launches()
     for i in range(K):
@@ -520,10 +537,11 @@ def run_ours(args):
             _, a5 = actions(cnt5, 4, 100 + rank)
             reps5 = 1 if 2 * cnt5 * N_IND * 2560 > (126 << 20) else 2  # one population pair already exceeds L2
             envs5, t5, th5, _ = vec_value_leg(h, env_factory(tot), a5, k5, 3, reps5)
+            how5 = envs5[0].collective if world > 1 else None
             del envs5, a5
             torch.cuda.empty_cache()
             c5[name] = {"workload": f"C5 vector env: {tot} envs over {world} GPU(s) ({cnt5} per GPU) x {N_IND} x {N_MARKERS}, "
-                                    f"NCCL reward all-gather" + (" (ncclAllGather through bg_allgather_f32)" if world > 1 else " (single GPU: no collective)"),
+                                    + (f"reward exchange: {how5}" if world > 1 else "single GPU: no exchange"),
                         "envs_total": tot, "envs_per_gpu": cnt5, "n_gpus": world, "steps": k5,
                         "value": tot * k5 / t5, "unit": UNIT, "ms_per_step": 1e3 * t5 / k5, "host_us_per_step": 1e6 * th5 / k5,
                         "scaling": "weak" if name.startswith("weak") else "strong",
@@ -553,7 +571,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * t_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 bit planes (cross) + int64 fixed point (GEBV)", "data": "synthetic",
-            "config": config_dict(world, replicas),
+            "config": dict(config_dict(world, replicas), **({"reward_exchange": reward_exchange} if world > 1 else {})),
             "offspring_markers_per_sec": value * N_IND * N_MARKERS,
             "host_us_per_step": 1e6 * t_host / K,
             "clocks": clocks,

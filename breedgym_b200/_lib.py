@@ -18,6 +18,7 @@ LIB_PATH = Path(os.environ.get("BG_LIB_PATH") or Path(__file__).resolve().parent
 
 LAYOUT_ID = {"legacy": 0, "partitionable": 1}
 SCHEDULE_ID = {"S1": 1, "S2": 2}
+PEER_HANDLE_BYTES = 96  # BG_PEER_HANDLE_BYTES
 
 _ERRORS = {-1: ValueError, -2: RuntimeError, -3: MemoryError, -4: ValueError, -5: RuntimeError}
 
@@ -65,6 +66,17 @@ _SIGNATURES = {
     "bg_comm_create": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),
     "bg_comm_destroy": (c_int, [c_void_p]),
     "bg_allgather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "bg_peer_create": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, POINTER(c_void_p)]),
+    "bg_peer_handle": (c_int, [c_void_p, c_void_p]),
+    "bg_peer_connect": (c_int, [c_void_p, c_void_p]),
+    "bg_engine_set_peer": (c_int, [c_void_p, c_void_p]),
+    "bg_peer_publish_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "bg_peer_wait": (c_int, [c_void_p, c_void_p]),
+    "bg_peer_epoch": (c_int64, [c_void_p]),
+    "bg_peer_result": (c_void_p, [c_void_p, c_int]),
+    "bg_peer_set_timeout_ms": (c_int, [c_void_p, c_int64]),
+    "bg_peer_timeouts": (c_int64, [c_void_p]),
+    "bg_peer_destroy": (c_int, [c_void_p]),
 }
 
 _lib = None

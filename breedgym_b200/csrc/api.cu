@@ -254,6 +254,7 @@ static void free_map(bg_engine *e)
 int bg_engine_destroy(bg_engine *eng)
 {
     if (!eng) return BG_OK;
+    bg_peer_engine_gone(eng);
     {
         DeviceGuard g(eng->device);
         free_map(eng);
@@ -880,7 +881,9 @@ int bg_vec_step(bg_engine *eng, const uint32_t *pop, uint32_t *out, const int32_
     key_state[1] = state[1];
     tm.lap(tm_on, 1);
     if (reward_dev) {
-        rc = bg_launch_reduce(gebv_dev, E, n * eng->T, reward_dev, 0, st);
+        // with a peer exchange attached (env-sharded run) the reduction also stores the rewards into every rank's window
+        rc = eng->peer ? bg_launch_reduce_publish(gebv_dev, E, n * eng->T, reward_dev, eng->peer, st)
+                       : bg_launch_reduce(gebv_dev, E, n * eng->T, reward_dev, 0, st);
         if (rc) return rc;
     }
     bool sync = false;

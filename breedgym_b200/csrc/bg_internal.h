@@ -86,6 +86,7 @@ struct bg_engine {
     size_t acc_cap = 0;                 // elements
     unsigned long long *d_acc2[2] = {nullptr, nullptr};  // gebv_tc2: all-zero between launches (one set per stream)
     size_t acc2_cap[2] = {0, 0};
+    struct bg_peer *peer = nullptr;     // reward exchange over peer memory (peer.cu): bg_vec_step publishes its rewards through it
     size_t tc2_optin[3] = {48 * 1024, 48 * 1024, 48 * 1024};  // dynamic smem already opted into (GEBV short-K, fused kernel, GEBV long-K)
 };
 
@@ -138,6 +139,10 @@ int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float 
 bool bg_cross_gebv_fused_ok(const bg_engine *eng, int64_t E, int64_t n_src, int64_t n);
 int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
                                int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st);
+
+// peer.cu
+int bg_launch_reduce_publish(const float *in, int64_t E, int64_t per_env, float *out, bg_peer *peer, cudaStream_t st);
+void bg_peer_engine_gone(bg_engine *eng);
 
 // topk.cu
 int bg_launch_topk(const float *scores, int64_t rows, int64_t len, int k, float *vals_out, int32_t *idx_out, cudaStream_t st);

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BG_VERSION 200
+#define BG_VERSION 210
 
 #define BG_OK 0
 #define BG_EINVAL (-1)   /* bad argument */
@@ -250,6 +250,46 @@ int bg_comm_unique_id(uint8_t id_out[BG_COMM_ID_BYTES]);
 int bg_comm_create(bg_engine *eng, const uint8_t id[BG_COMM_ID_BYTES], int world, int rank, bg_comm **out);
 int bg_comm_destroy(bg_comm *comm);
 int bg_allgather_f32(bg_comm *comm, const float *send_dev, float *recv_dev, int64_t count, void *stream);
+
+/* ---- reward exchange over peer memory (multi-GPU, one NVSwitch box) ---------------
+ * The same exchange WITHOUT a collective launch: the kernel that reduces a step's
+ * GEBVs to per-env rewards (breedgym/vector/vec_env.py:95-100) stores each reward
+ * straight into a small receive window on EVERY rank (peer-to-peer stores over
+ * NVLink) and, once all of this rank's rewards are out, raises the rank's epoch flag
+ * in every window.  No NCCL kernel, no extra launch, no host work at an episode's
+ * end; a consumer orders itself behind the exchange with bg_peer_wait (a one-warp
+ * kernel that spins on the local flags).  Replaces the reward half of
+ * DistributedBreedGym's step_wait (vec_env.py:197-219).
+ *   every rank: bg_peer_create(eng, world, rank, total, offset, &peer)  (`total` rewards over all
+ *   ranks, this rank owns [offset, offset + its E): ragged shards are fine); bg_peer_handle(peer, h)
+ *   -> all-gather the BG_PEER_HANDLE_BYTES of every rank on the host (any channel)
+ *   -> every rank: bg_peer_connect(peer, handles)   (CUDA IPC; ranks that live in the
+ *   same process are connected through their raw pointers)
+ *   -> bg_engine_set_peer(eng, peer): from now on every bg_vec_step of that engine
+ *   with reward_dev != NULL publishes its E rewards as the next EPOCH.
+ * Window of epoch k: float32[total] (env order) at bg_peer_result(peer, k & 1).
+ * Flow control: epoch k is written only after every rank has published epoch k - 1,
+ * so the rewards of an episode stay valid on a rank until that rank ends its next
+ * episode.  All spins are bounded (option below): a rank that never arrives is
+ * counted in bg_peer_timeouts instead of hanging the GPU.  The window itself is
+ * never freed before the process exits (late peers must not fault). */
+typedef struct bg_peer bg_peer;
+#define BG_PEER_HANDLE_BYTES 96
+#define BG_PEER_MAX_WORLD 16
+int bg_peer_create(bg_engine *eng, int world, int rank, int64_t total, int64_t offset, bg_peer **out);
+int bg_peer_handle(bg_peer *peer, uint8_t handle_out[BG_PEER_HANDLE_BYTES]);
+int bg_peer_connect(bg_peer *peer, const uint8_t *handles /* [world][BG_PEER_HANDLE_BYTES] */);
+int bg_engine_set_peer(bg_engine *eng, bg_peer *peer /* NULL: detach */);
+/* standalone publish of this rank's float32[count] as the next epoch, for rewards that
+ * were not reduced by bg_vec_step */
+int bg_peer_publish_f32(bg_peer *peer, const float *send_dev, int64_t count, void *stream);
+/* make `stream` wait (on the device) until every rank's slice of the LAST published epoch has landed */
+int bg_peer_wait(bg_peer *peer, void *stream);
+int64_t bg_peer_epoch(bg_peer *peer);                 /* epochs published so far by this rank */
+float *bg_peer_result(bg_peer *peer, int parity);     /* device pointer: float32[total] of epochs with k & 1 == parity */
+int bg_peer_set_timeout_ms(bg_peer *peer, int64_t ms); /* bound of every device-side spin (default 20 000) */
+int64_t bg_peer_timeouts(bg_peer *peer);              /* spins that hit the bound so far (synchronises the device) */
+int bg_peer_destroy(bg_peer *peer);
 
 #ifdef __cplusplus
 }

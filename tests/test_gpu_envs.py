@@ -398,6 +398,53 @@ def test_empty_cross_and_single_offspring(cuda_device):
     assert np.array_equal(np.asarray(kid), homo)
 
 
+def test_peer_reward_exchange_two_shards_in_one_process(cuda_device):
+    """The reward exchange over peer memory (csrc/peer.cu) with both "ranks" on this GPU: shards [0,3) and [3,5) of a
+    5-env run publish their rewards from inside bg_vec_step's reduction into both windows; every shard then reads the
+    5-env VecBreedGym's rewards (device mode: ragged window; three episode ends, so both window halves are re-used
+    and the flow control runs), and the standalone publish gives the same."""
+    import torch
+
+    from breedgym_b200.vector import ShardedVecBreedGym, VecBreedGym
+
+    n = 50
+    kw = dict(initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n, num_generations=3, info_device="device")
+    full = VecBreedGym(num_envs=5, **kw)
+    shards = [ShardedVecBreedGym(total_envs=5, world=2, rank=r, async_rewards=True, **kw) for r in range(2)]
+    ShardedVecBreedGym.connect_local(shards)
+    for s in shards:
+        assert s.collective == "peer"
+        s._peer.set_timeout_ms(2000)
+        s.reset(seed=11)
+    full.reset(seed=11)
+    rng = np.random.default_rng(0)
+    dev = full.device
+    n_rewards = 0
+    for step in range(10):
+        act = torch.from_numpy(rng.integers(0, n, (5, n, 2)).astype(np.int32)).to(dev)
+        pf, rf, _, tf, _ = full.step(act)
+        outs = [s.step(act[s.local_slice()].contiguous()) for s in shards]
+        for s in shards:
+            s.wait_rewards()
+        assert np.array_equal(np.asarray(pf), np.concatenate([np.asarray(o[0]) for o in outs]))
+        for o in outs:
+            assert o[1].shape == (5,) and torch.equal(o[1], rf), f"step {step}"
+            assert np.array_equal(o[3], tf)
+        n_rewards += bool(tf[0])
+    assert n_rewards == 3
+    # rewards that did not come out of a step: publish + wait
+    vals = [torch.arange(3, dtype=torch.float32, device=dev) + 10, torch.arange(2, dtype=torch.float32, device=dev) + 20]
+    got = [s.gather_rewards(v) for s, v in zip(shards, vals)]
+    for s in shards:
+        s.wait_rewards()
+    got = [s._window() for s in shards]
+    for g in got:
+        assert torch.equal(g, torch.cat(vals))
+    assert all(s._peer.timeouts() == 0 for s in shards)
+    for s in shards:
+        s.close()
+
+
 def test_sharded_env_over_nccl_matches_unsharded(cuda_device):
     """Two ranks on two GPUs (skipped on a single-GPU box): scripts/multi_gpu_check.py under torchrun."""
     import subprocess

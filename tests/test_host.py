@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/breedgym_b200.h but not exported"
     assert declared == set(_lib._SIGNATURES), "ctypes signatures out of sync with the header"
-    assert lib.bg_version() == 200
+    assert lib.bg_version() == 210
 
 
 def test_gpu_calls_fail_loudly_without_a_device():
