@@ -178,7 +178,8 @@ int bg_engine_create(int device, bg_engine **out)
     cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     // tuning switches: the environment is read HERE, once (BG_OPT_<NAME>); nothing on the step path calls getenv
     static const char *const names[] = {"fuse", "gebv_algo", "lookahead", "mask_nt", "mask_big_ctas", "mask_ctas_per_sm", "blend_env_chunk",
-                                        "copy_engine", "mapped_d2h_max", "tc_target_ctas", "timing", "gebv_digits", "gebv_shape", "rows_nt"};
+                                        "copy_engine", "mapped_d2h_max", "tc_target_ctas", "timing", "gebv_digits", "gebv_shape", "rows_nt", "fused_dyn", "step_pdl",
+                                        "xg_parts"};
     for (const char *name : names) {
         std::string env = "BG_OPT_";
         for (const char *c = name; *c; ++c) env += (char)toupper(*c);
@@ -220,6 +221,12 @@ int bg_engine_set_option(bg_engine *eng, const char *name, int64_t value)
     else if (n == "mapped_d2h_max") o.mapped_d2h_max = value;
     else if (n == "tc_target_ctas") o.tc_target_ctas = value;
     else if (n == "timing") o.timing = value != 0;
+    else if (n == "fused_dyn") o.fused_dyn = value < 0 ? -1 : (value != 0);
+    else if (n == "step_pdl") o.step_pdl = value != 0;
+    else if (n == "xg_parts") {
+        BG_REQUIRE(value >= 0 && value < 100000000, BG_EINVAL, "xg_parts: up to 8 decimal digits");
+        o.xg_parts = value;
+    }
     else if (n == "rows_nt") {
         BG_REQUIRE(value == 0 || (value >= 64 && value <= 1024 && value % 32 == 0), BG_EINVAL, "rows_nt must be 0 or a multiple of 32 in 64..1024");
         o.rows_nt = (int)value;
@@ -272,6 +279,7 @@ int bg_engine_destroy(bg_engine *eng)
         if (eng->reset_ready) cudaEventDestroy(eng->reset_ready);
         cudaFree(eng->d_mut);
         cudaFree(eng->d_acc);
+        cudaFree(eng->d_xg_work);
         for (int i = 0; i < 2; ++i) {
             cudaFree(eng->d_acc2[i]);
         }
@@ -615,7 +623,11 @@ static int cross_envs_impl(bg_engine *eng, const uint32_t *pop, const int32_t *p
     // One fused cross+GEBV kernel (cross_gebv.cu) whenever the tensor-core path applies; option fuse=0 selects the
     // two-kernel path (cross-checks, tuning).
     if (gebv_out && eng->opt.fuse && bg_cross_gebv_fused_ok(eng, E, n_src, n)) {
-        rc = bg_launch_cross_gebv_fused(eng, pop, parents, mask, out, E, n_src, n, gebv_out, st);
+        const int64_t tiles = (E * n + 127) / 128;
+        const bool dyn = eng->opt.fused_dyn > 0 || (eng->opt.fused_dyn < 0 && tiles >= 8LL * eng->sm_count);
+        rc = (dyn && bg_cross_gebv_dyn_ok(eng, E, n_src, n))
+                 ? bg_launch_cross_gebv_dyn(eng, pop, parents, mask, out, E, n_src, n, gebv_out, st)
+                 : bg_launch_cross_gebv_fused(eng, pop, parents, mask, out, E, n_src, n, gebv_out, st);
     } else {
         // blend and GEBV are adjacent in the stream (no event between them) so that the GEBV kernel's
         // programmatic dependent launch can overlap its prologue with the blend's tail

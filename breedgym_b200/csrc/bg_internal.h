@@ -52,6 +52,10 @@ struct bg_options {
     int timing = 0;
     int gebv_shape = 0;        // tensor-core GEBV pipeline shape: 0 auto, 1 short-K <SPM 1, S 3>, 2 long-K <SPM 2, S 4>
     int gebv_digits = 0;       // 0: as many base-256 digits as the map needs; 8: always 8 (cross-checks)
+    int step_pdl = 1;          // programmatic dependent launch of the step kernels (their prologue overlaps the previous step's tail)
+    int fused_dyn = -1;        // the persistent fused step kernel with a dynamic work queue (cross_gebv_dyn.cu): 1 always, 0 never,
+                               // -1 when a launch has >= 4 tiles per resident CTA (measured: 256 vs 275 us at 512 envs, 43 vs 40 us at 64)
+    long long xg_parts = 0;    // its split of a tile's K range, proportions as decimal digits (8642 = 8:6:4:2); 0: auto
 };
 
 struct bg_engine {
@@ -87,7 +91,9 @@ struct bg_engine {
     unsigned long long *d_acc2[2] = {nullptr, nullptr};  // gebv_tc2: all-zero between launches (one set per stream)
     size_t acc2_cap[2] = {0, 0};
     struct bg_peer *peer = nullptr;     // reward exchange over peer memory (peer.cu): bg_vec_step publishes its rewards through it
-    size_t tc2_optin[3] = {48 * 1024, 48 * 1024, 48 * 1024};  // dynamic smem already opted into (GEBV short-K, fused kernel, GEBV long-K)
+    unsigned int *d_xg_work = nullptr;  // work counters of the persistent fused step kernel (cross_gebv_dyn.cu)
+    unsigned xg_seq = 0;
+    size_t tc2_optin[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};  // dynamic smem already opted into (GEBV short-K, fused kernel, GEBV long-K, persistent fused kernel)
 };
 
 void bg_set_error(const std::string &msg);
@@ -137,6 +143,9 @@ int bg_launch_reduce(const float *in, int64_t E, int64_t per_env, float *out, in
 // gebv_tc2.cu: TMA tile loads + operand A in tensor memory
 int bg_launch_gebv_tc2(bg_engine *eng, const uint32_t *pop, int64_t rows, float *out, cudaStream_t st, int scratch = 0);
 bool bg_cross_gebv_fused_ok(const bg_engine *eng, int64_t E, int64_t n_src, int64_t n);
+bool bg_cross_gebv_dyn_ok(const bg_engine *eng, int64_t E, int64_t n_src, int64_t n);
+int bg_launch_cross_gebv_dyn(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
+                             int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st);
 int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_t *parents, const uint32_t *mask, uint32_t *out_pop,
                                int64_t E, int64_t n_src, int64_t n, float *gebv_out, cudaStream_t st);
 

@@ -90,10 +90,13 @@ constexpr uint32_t XG_NOROW = 0xFFFFFFFFu;
 #ifndef XG_TRACE_CTA
 #define XG_TRACE_CTA 0
 #endif
+#ifndef XG_TRACE_Y
+#define XG_TRACE_Y 0
+#endif
 __device__ long long xg_trace_buf[16 * 64];
 #define XG_STAMP(slot, idx)                                                                                              \
     do {                                                                                                                 \
-        if (blockIdx.x == XG_TRACE_CTA && blockIdx.y == 0 && (idx) < 64) xg_trace_buf[(slot) * 64 + (idx)] = clock64(); \
+        if (blockIdx.x == XG_TRACE_CTA && blockIdx.y == XG_TRACE_Y && (idx) < 64) xg_trace_buf[(slot) * 64 + (idx)] = clock64(); \
     } while (0)
 #else
 #define XG_STAMP(slot, idx) \
@@ -160,6 +163,14 @@ __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) XG_STAMP(15, 0);
+    // Programmatic dependent launch, both ends.  (1) The NEXT step kernel of the stream may be scheduled as soon as every
+    // CTA of this grid has started: its CTAs take the slots this grid's last wave leaves idle and run their prologue
+    // (tensor-memory allocation, barrier init, row table from the action array) while this grid drains.  (2) This
+    // kernel's own prologue below touches nothing an earlier kernel of the stream writes -- the action array is an
+    // INPUT of the step, produced before the previous step kernel was launched or by a kernel that does not trigger
+    // early -- and everything after `griddepcontrol.wait` (populations, masks, accumulators, outputs) sees the
+    // completed, flushed predecessor.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t in_base = smem_u32(smem);
     const uint32_t mask_base = in_base + XG_R * XG_IN_BYTES;
     const uint32_t b_base0 = mask_base + XG_R * XG_MASK_BYTES;
@@ -223,6 +234,7 @@ __global__ void __launch_bounds__(XG_REGCAP_THREADS, XG_CTAS)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // a no-op unless launched with programmatic stream serialization
     const uint32_t tmem_d = tmem_base_slot;
     const uint32_t tmem_a = tmem_d + d_cols;
 
@@ -503,8 +515,22 @@ int bg_launch_cross_gebv_fused(bg_engine *eng, const uint32_t *pop, const int32_
     fa.rows = rows;
     fa.W4 = eng->Wpad / 4;
     dim3 grid((unsigned)tiles, (unsigned)ksplit);
-    cross_gebv_kernel<<<grid, XG_THREADS, smem, st>>>(fa, eng->d_wdig, N, T, eng->tc_D, nbp, steps, sps, eng->d_acc2[0],
-                                                      eng->d_inv_scale, gebv_out);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(XG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = eng->opt.step_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int8_t *bd = eng->d_wdig;
+    const int D = eng->tc_D;
+    unsigned long long *accp = eng->d_acc2[0];
+    const double *inv = eng->d_inv_scale;
+    BG_CUDA(cudaLaunchKernelEx(&cfg, cross_gebv_kernel, fa, bd, N, T, D, nbp, steps, sps, accp, inv, gebv_out));
     BG_LAUNCHED();
     return BG_OK;
 }

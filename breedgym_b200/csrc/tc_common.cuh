@@ -8,7 +8,10 @@ namespace bgtc {
 
 constexpr int TILE_M = 128;     // individuals per tile (TMEM lanes)
 constexpr int STEP_K = 128;     // markers per step (4 words per plane, 32 TMEM columns of int8x4)
-constexpr uint32_t SPIN_LIMIT = 1u << 28;
+#ifndef BG_SPIN_LIMIT
+#define BG_SPIN_LIMIT (1u << 28)   // mbarrier waits trap after this many try_wait rounds (diagnostic builds lower it)
+#endif
+constexpr uint32_t SPIN_LIMIT = BG_SPIN_LIMIT;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

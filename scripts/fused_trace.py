@@ -35,12 +35,18 @@ for _ in range(5):
     torch.cuda.synchronize()
 raw = ctypes.CDLL(str(_lib.LIB_PATH))
 buf = np.zeros(16 * 64, dtype=np.int64)
-raw.bg_debug_read_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
-assert raw.bg_debug_read_trace(buf.ctypes.data, buf.size) == 0
+reader = raw.bg_debug_read_trace_dyn if os.environ.get("BG_OPT_FUSED_DYN") == "1" else raw.bg_debug_read_trace
+reader.argtypes = [ctypes.c_void_p, ctypes.c_int]
+assert reader(buf.ctypes.data, buf.size) == 0
 t = buf.reshape(16, 64)
 t0 = t[15, 0]
-names = ["st done warp0 (g0)", "st done warp1", "raw_full g0", "raw_full g1", "st done warp2", "4 MMAs issued", "fields done (g0 steps)",
-         "a_empty seen", "tmem st done", "st done warp3", "B half landed", "A full", "MMA issued", "gather issued", "stage_done seen", "cta"]
+names = ["tmem st published w0", "w1", "raw_full g0", "raw_full g1", "w2", "8 MMAs issued (pair)", "fields done (step)",
+         "a_empty seen (step)", "tmem st done (step)", "w3", "digit pair landed", "A pair full", "commits issued", "gather issued (stage)",
+         "stage_done seen (stage)", "cta start/roles done/acc done/epilogue done"]
+if os.environ.get("BG_OPT_FUSED_DYN") == "1":  # the persistent kernel (cross_gebv_dyn.cu) stamps other events
+    names = ["parents in registers (@stage)", "acc seen / epilogue done (2 per item)", "raw_full g0 (stage)", "raw_full g1", "loaders start item",
+             "expanders g0 start item", "MMA starts item", "expanders g1 start item", "tmem st done (step)", "next item known (item)",
+             "digit pair landed", "A pair full", "commits issued", "gather issued (stage)", "stage_done seen (stage)", "cta start/-/-/end"]
 for s in range(16):
-    vals = [int(v - t0) for v in t[s] if v != 0]
-    print(f"{s:2d} {names[s]:24s}", " ".join(f"{v:6d}" for v in vals[:32]))
+    vals = [(i, int(v - t0)) for i, v in enumerate(t[s]) if v != 0]
+    print(f"{s:2d} {names[s]:36s}", " ".join(f"{i}:{v}" for i, v in vals[:40]))
