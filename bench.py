@@ -321,7 +321,7 @@ class Harness:
         return start.elapsed_time(end) * 1e-3, host
 
 
-def vec_value_leg(h, make_env, acts_dev, K, W, replicas, sample_clocks=None):
+def vec_value_leg(h, make_env, acts_dev, K, W, replicas, sample_clocks=None, steady_steps=0):
     """Device-resident step loop: `replicas` independent envs round-robin.  Warm-up runs every replica through a
     whole episode (autoreset and the reward all-gather included) plus one untimed rehearsal of the K steps, so the
     timed K steps carry the steady one-in-`num_generations` reset rate on warm code paths."""
@@ -346,7 +346,14 @@ def vec_value_leg(h, make_env, acts_dev, K, W, replicas, sample_clocks=None):
         sample_clocks.start()
     t_dev, t_host = h.timed(step, K, finish)
     clocks = sample_clocks.stop() if sample_clocks is not None else None
-    return envs, h.max_over_ranks(t_dev), t_host, clocks
+    steady = None
+    if steady_steps and steady_steps > K:
+        # the same loop over a window long enough to carry the steady-state share of everything that runs beside the
+        # steps (a K = 20 window starts on crossover masks the rehearsal left ready; over a long run the mask kernel of
+        # the FOLLOWING batches competes with the step kernels for issue slots all the time)
+        ts_dev, ts_host = h.timed(step, steady_steps, finish)
+        steady = (h.max_over_ranks(ts_dev), ts_host, steady_steps)
+    return envs, h.max_over_ranks(t_dev), t_host, clocks, steady
 
 
 def run_ours(args):
@@ -404,7 +411,8 @@ def run_ours(args):
     # ---------------- value: device-resident inputs, pipelined, inputs larger than L2 ----------------
     sampler = ClockSampler(local_rank)
     launches0 = lib.bg_kernel_launches()
-    envs, t_value, t_host, clocks = vec_value_leg(h, env_factory(total_envs), acts_dev, K, W, replicas, sampler)
+    envs, t_value, t_host, clocks, steady = vec_value_leg(h, env_factory(total_envs), acts_dev, K, W, replicas, sampler,
+                                                          steady_steps=args.steady_steps)
     launches_total = lib.bg_kernel_launches() - launches0
     reward_exchange = None
     if world > 1:
@@ -531,6 +539,7 @@ def run_ours(args):
     if args.skip_e2e:
         if rank == 0:
             print(json.dumps({"value": total_envs * K / t_value, "ms_per_step": 1e3 * t_value / K, "replicas": replicas,
+                              "steady_ms_per_step": None if steady is None else 1e3 * steady[0] / steady[2],
                               "host_us_per_step": 1e6 * t_host / K, "kernels_ms": bk}), flush=True)
         return 0
     make_env = env_factory(total_envs)
@@ -569,7 +578,7 @@ def run_ours(args):
             b5, cnt5 = shard_range(tot, world, rank)
             _, a5 = actions(cnt5, 4, 100 + rank)
             reps5 = 1 if 2 * cnt5 * N_IND * 2560 > (126 << 20) else 2  # one population pair already exceeds L2
-            envs5, t5, th5, _ = vec_value_leg(h, env_factory(tot), a5, k5, 3, reps5)
+            envs5, t5, th5, _, _ = vec_value_leg(h, env_factory(tot), a5, k5, 3, reps5)
             how5 = envs5[0].collective if world > 1 else None
             del envs5, a5
             torch.cuda.empty_cache()
@@ -607,6 +616,11 @@ def run_ours(args):
             "config": dict(config_dict(world, replicas), **({"reward_exchange": reward_exchange} if world > 1 else {})),
             "offspring_markers_per_sec": value * N_IND * N_MARKERS,
             "host_us_per_step": 1e6 * t_host / K,
+            "steady_state": None if steady is None else {
+                "steps": steady[2], "value": total_envs * steady[2] / steady[0], "unit": UNIT, "ms_per_step": 1e3 * steady[0] / steady[2],
+                "host_us_per_step": 1e6 * steady[1] / steady[2],
+                "note": "the same device-resident loop over a long window: carries the full share of the crossover-mask "
+                        "generation (Threefry, integer-issue bound) that runs beside the step kernels"},
             "clocks": clocks,
             "e2e": {"value": total_envs * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "VecBreedGym.step(numpy actions) -> numpy GEBV / rewards, one sync per step",
@@ -653,6 +667,8 @@ def main():
     ap.add_argument("--no-legs", action="store_true", help="skip the C1 / C3 / C4 legs")
     ap.add_argument("--replicas", type=int, default=REPLICAS, help="independent workload copies stepped round-robin")
     ap.add_argument("--skip-e2e", action="store_true", help="diagnostics: only the device-resident value")
+    ap.add_argument("--steady-steps", type=int, default=2000,
+                    help="length of the extra long-run window reported as steady_state (0: skip; skipped when --steps is longer)")
     ap.add_argument("--stream-priority", type=int, default=-1,
                     help="priority of the CUDA stream the steps run on (default -1: above the library's mask side stream; 0: torch's current stream)")
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU,

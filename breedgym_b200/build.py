@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libbreedgym_b200.so"
 OBJ_DIR = PKG / "_obj"
-SOURCES = ["api.cu", "meiosis.cu", "gebv.cu", "gebv_tc2.cu", "cross_gebv.cu", "cross_gebv_dyn.cu", "layout.cu", "comm.cu", "topk.cu", "peer.cu"]
+SOURCES = ["api.cu", "meiosis.cu", "gebv.cu", "gebv_tc2.cu", "cross_gebv.cu", "cross_gebv_dyn.cu", "layout.cu", "comm.cu", "topk.cu", "peer.cu", "pairs.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -274,6 +274,8 @@ int bg_engine_destroy(bg_engine *eng)
             cudaFree(b.mut);
             if (b.ready) cudaEventDestroy(b.ready);
             if (b.freed) cudaEventDestroy(b.freed);
+            if (b.t0) cudaEventDestroy(b.t0);
+            if (b.t1) cudaEventDestroy(b.t1);
         }
         if (eng->tmp_event) cudaEventDestroy(eng->tmp_event);
         if (eng->reset_ready) cudaEventDestroy(eng->reset_ready);
@@ -513,8 +515,24 @@ static int batch_generate(bg_engine *eng, int bi, int count, const uint32_t (*ke
             if (rc) return rc;
         }
     }
+    if (eng->opt.timing) {  // diagnostics: device time of the previous generation into this buffer
+        if (!b.t0) {
+            BG_CUDA(cudaEventCreate(&b.t0));
+            BG_CUDA(cudaEventCreate(&b.t1));
+        }
+        if (b.timed) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(b.t1) == cudaSuccess && cudaEventElapsedTime(&ms, b.t0, b.t1) == cudaSuccess)
+                fprintf(stderr, "[bg mask batch] %d keys x %lld rows generated in %.1f us\n", b.count, (long long)b.rows, 1e3 * ms);
+        }
+        BG_CUDA(cudaEventRecord(b.t0, on));
+    }
     int rc = bg_launch_mask_batch(eng, rows, count, keys, layout, schedule, b.mask, eng->mut_thr ? b.mut : nullptr, on, small_ctas);
     if (rc) return rc;
+    if (eng->opt.timing) {
+        BG_CUDA(cudaEventRecord(b.t1, on));
+        b.timed = true;
+    }
     BG_CUDA(cudaEventRecord(b.ready, on));
     b.gen_stream = on;
     b.synced_stream = on;  // work enqueued on `on` later is ordered behind the kernel anyway
@@ -733,6 +751,22 @@ int bg_topk(bg_engine *eng, const float *scores, int64_t rows, int64_t len, int3
     BG_ENTER(eng);
     BG_REQUIRE(rows >= 0 && len >= 0 && (rows == 0 || (scores && vals_out && idx_out)), BG_EINVAL, "bg_topk: bad argument");
     return bg_launch_topk(scores, rows, len, k, vals_out, idx_out, (cudaStream_t)stream);
+}
+
+int bg_pairs_from_topk(bg_engine *eng, const float *vals, const int32_t *idx, int64_t E, int32_t k, int64_t row_len, int32_t *pairs_out,
+                       void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(E >= 0 && (E == 0 || (vals && idx && pairs_out)), BG_EINVAL, "bg_pairs_from_topk: bad argument");
+    return bg_launch_pairs_from_topk(vals, idx, E, k, row_len, pairs_out, (cudaStream_t)stream);
+}
+
+int bg_diallel_pairs(bg_engine *eng, const int32_t *best, const int32_t *perm, int64_t E, int32_t k, int32_t nc, int64_t n,
+                     int32_t *pairs_out, void *stream)
+{
+    BG_ENTER(eng);
+    BG_REQUIRE(E >= 0 && (E == 0 || (best && perm && pairs_out)), BG_EINVAL, "bg_diallel_pairs: bad argument");
+    return bg_launch_diallel_pairs(best, perm, E, k, nc, n, pairs_out, (cudaStream_t)stream);
 }
 
 int bg_reset_indices(bg_engine *eng, const uint32_t random_key[2], int64_t E_total, int64_t env_begin, int64_t E, int64_t n_germ,

@@ -31,6 +31,8 @@ struct bg_mask_batch {
     cudaStream_t use_stream = nullptr;          // stream of the readers since the last `freed` record
     bool used = false;
     unsigned long long stamp = 0;               // last use (LRU choice of the buffer to refill)
+    cudaEvent_t t0 = nullptr, t1 = nullptr;     // option timing: around the generating kernel
+    bool timed = false;
 };
 
 constexpr int BG_MASK_BATCHES = 3;
@@ -155,6 +157,10 @@ void bg_peer_engine_gone(bg_engine *eng);
 
 // topk.cu
 int bg_launch_topk(const float *scores, int64_t rows, int64_t len, int k, float *vals_out, int32_t *idx_out, cudaStream_t st);
+
+// pairs.cu
+int bg_launch_pairs_from_topk(const float *vals, const int32_t *idx, int64_t E, int k, int64_t row_len, int32_t *out, cudaStream_t st);
+int bg_launch_diallel_pairs(const int32_t *best, const int32_t *perm, int64_t E, int k, int nc, int64_t n, int32_t *out, cudaStream_t st);
 
 // layout.cu
 int bg_launch_copy_mapped(const void *src, void *dst, size_t bytes, cudaStream_t st);

@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : (NT_MAX == 512 ? 2
     }
     __syncthreads();
 
+#if defined(BG_FAKE_CONST_THR)   // timing experiment only (wrong masks): what do the threshold loads cost beside the step kernel?
+    draw_bits<LAYOUT, true>(S, krec, nullptr, nullptr, 12000u, m, lane, warp, NW, P.one);
+#else
     draw_bits<LAYOUT, false>(S, krec, P.thr, P.thr_cmp, 0u, m, lane, warp, NW, P.one);
+#endif
     if (has_mut) draw_bits<LAYOUT, true>(Mu, kmut, nullptr, nullptr, P.mut_thr, m, lane, warp, NW, P.one);
     __syncthreads();
 

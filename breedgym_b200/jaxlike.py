@@ -47,6 +47,32 @@ def choice_no_replace(key: np.ndarray, n_inputs: int, n_draws: int, layout: str 
     return permutation(key, n_inputs, layout)[:n_draws]
 
 
+def erf_inv_f32(x: np.ndarray) -> np.ndarray:
+    """`lax.erf_inv` in float32 (XLA's expansion: Giles' two degree-8 polynomials in w = -log1p(-x^2))."""
+    x = np.asarray(x, dtype=np.float32)
+    w = -np.log1p(-(x * x))
+    small = w < np.float32(5.0)
+    w = np.where(small, w - np.float32(2.5), np.sqrt(w) - np.float32(3.0)).astype(np.float32)
+    lo = (2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503, -0.00417768164,
+          0.246640727, 1.50140941)
+    hi = (-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613, 0.00943887047,
+          1.00167406, 2.83297682)
+    p = np.where(small, np.float32(lo[0]), np.float32(hi[0])).astype(np.float32)
+    for a, b in zip(lo[1:], hi[1:]):
+        p = (np.where(small, np.float32(a), np.float32(b)) + p * w).astype(np.float32)
+    out = (p * x).astype(np.float32)
+    return np.where(np.abs(x) == 1, np.copysign(np.float32(np.inf), x), out).astype(np.float32)
+
+
+def normal(key: np.ndarray, n: int, layout: str = "legacy") -> np.ndarray:
+    """`jax.random.normal(key, (n,))` in float32: sqrt(2) * erf_inv(u), u uniform on (-1, 1) from the key's bits."""
+    bits = _lib.random_bits(key, n, layout)
+    f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    lo = np.nextafter(np.float32(-1.0), np.float32(0.0))
+    u = np.maximum(lo, (f * (np.float32(1.0) - lo) + lo).astype(np.float32))
+    return (np.float32(np.sqrt(2)) * erf_inv_f32(u)).astype(np.float32)
+
+
 def top_k(x: np.ndarray, k: int):
     """`jax.lax.top_k` along the last axis: descending, ties -> lower index."""
     x = np.asarray(x)

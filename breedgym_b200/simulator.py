@@ -27,16 +27,34 @@ from .population import PackedPopulation, ParentsView
 class TraitModel:
     """chromax.trait_model.TraitModel: `dot(sum(pop, -1), effects) + offset`."""
 
-    def __init__(self, sim: "Simulator", marker_effects: np.ndarray, offset: float = 0.0):
+    def __init__(self, sim: "Simulator", marker_effects: np.ndarray, offset: float = 0.0, own_engine: bool = False):
         self._sim = sim
         self.marker_effects = np.ascontiguousarray(marker_effects, dtype=np.float32)
         self.offset = offset
         self.n_traits = self.marker_effects.shape[1]
+        # a model other than the simulator's GEBV model (the GxE model) scores through an engine of its own: the same
+        # kernels over its own fixed-point effect tables
+        self._engine = None
+        if own_engine:
+            self._engine = ctypes.c_void_p()
+            lib = _lib.load()
+            _lib.check(lib.bg_engine_create(sim.device.index, ctypes.byref(self._engine)))
+            _lib.check(lib.bg_engine_set_map(self._engine, _lib.nptr(sim.recombination_vec), _lib.nptr(self.marker_effects),
+                                             sim.n_markers, self.n_traits, 0.0))
 
     def __call__(self, population) -> torch.Tensor:
         """`float32[..., n_traits]` on the simulator's device."""
-        out = self._sim._gebv(self._sim.as_packed(population))
+        out = self._sim._gebv(self._sim.as_packed(population), self._engine, self.n_traits)
         return out + self.offset if self.offset else out
+
+    def __del__(self):
+        eng = getattr(self, "_engine", None)
+        if eng:
+            try:
+                _lib.load().bg_engine_destroy(eng)
+            except Exception:
+                pass
+            self._engine = None
 
     @property
     def positive_mask(self) -> np.ndarray:
@@ -151,8 +169,13 @@ class Simulator:
         if seed is None:
             seed = random.randint(0, 2**32)
         self.random_key = _lib.key_data(seed)
-        # chromax draws the GxE effects at construction, consuming one split
-        self.random_key = self._split(self.random_key, 2)[0]
+        # chromax draws the GxE effects at construction, consuming one split: `random_key, split_key = split(random_key)`.
+        # The draw itself (m x T normals) is deferred until somebody asks for a phenotype (`GxE_model`).
+        halves = self._split(self.random_key, 2)
+        self.random_key = halves[0]
+        self._gxe_key = halves[1].copy()
+        self._gxe_model = None
+        self.h2 = np.full(len(self.trait_names), 0.5, dtype=np.float32) if h2 is None else np.asarray(h2, dtype=np.float32)
 
     def __del__(self):
         eng = getattr(self, "_engine", None)
@@ -237,13 +260,13 @@ class Simulator:
                                                      1, src.shape[0], n, 0, self._stream()))
         return PackedPopulation(self, out)
 
-    def _gebv(self, population: PackedPopulation) -> torch.Tensor:
+    def _gebv(self, population: PackedPopulation, engine=None, n_traits: Optional[int] = None) -> torch.Tensor:
         w = population.words.contiguous()
         lead = tuple(w.shape[:-2])
         rows = int(np.prod(lead))
-        T = self.GEBV_model.n_traits
+        T = self.GEBV_model.n_traits if n_traits is None else n_traits
         out = torch.empty((*lead, T), dtype=torch.float32, device=self.device)
-        _lib.check(_lib.load().bg_gebv(self._engine, w.data_ptr(), rows, out.data_ptr(), self._stream()))
+        _lib.check(_lib.load().bg_gebv(engine or self._engine, w.data_ptr(), rows, out.data_ptr(), self._stream()))
         return out
 
     def _top_k(self, values: torch.Tensor, k: int) -> torch.Tensor:
@@ -347,6 +370,43 @@ class Simulator:
         """`vmap(cross)(populations[arange, actions])` with ONE key for all envs
         (breedgym/vector/vec_env.py:75-77, 89-91)."""
         return self._cross_indexed(populations, actions, self._next_key())
+
+    # ---- phenotype / GxE (chromax Simulator.phenotype, create_environments; scripts/time_wheat.py:17-50) ----------
+    @property
+    def GxE_model(self) -> TraitModel:
+        """Genotype-by-environment effects: `normal(split_key, (m, T))` rescaled per trait to the variance
+        `(1 - h2) / h2 * GEBV_model.var`, offset 1 (chromax Simulator.__init__, recalled in SURVEY App. B -- parity
+        unpinned, like every chromax detail).  Built on first use, scored by the same kernels as the GEBV."""
+        if self._gxe_model is None:
+            from . import jaxlike
+
+            m, T = self.n_markers, len(self.trait_names)
+            env = jaxlike.normal(self._gxe_key, m * T, self.rng_layout).reshape(m, T)
+            target = (1 - self.h2) / self.h2 * self.GEBV_model.var
+            env = (env * np.sqrt(target / (np.sum(env**2, axis=0) / 2)).astype(np.float32)).astype(np.float32)
+            self._gxe_model = TraitModel(self, env, offset=1, own_engine=True)
+        return self._gxe_model
+
+    def create_environments(self, num_environments: int) -> np.ndarray:
+        """`random_key, k = split(random_key)`; `normal(k, (num_environments,))`: one scalar per environment."""
+        from . import jaxlike
+
+        k = self._next_key()
+        return jaxlike.normal(k, int(num_environments), self.rng_layout)
+
+    def phenotype(self, population, *, num_environments: Optional[int] = None, environments=None) -> torch.Tensor:
+        """Mean over the environments of `GEBV(pop) + env * GxE(pop)` -> `float32[..., n_traits]` on the device
+        (chromax `_phenotype`).  One environment is drawn when neither argument is given."""
+        if num_environments is not None and environments is not None:
+            raise ValueError("You cannot specify both the number of environments and the environments.")
+        if environments is None:
+            environments = self.create_environments(1 if num_environments is None else num_environments)
+        pop = self.as_packed(population)
+        g = self.GEBV_model(pop)
+        e = self.GxE_model(pop)
+        envs = torch.as_tensor(np.asarray(environments, dtype=np.float32).reshape(-1), device=self.device)
+        view = (-1,) + (1,) * g.dim()
+        return torch.mean(g.unsqueeze(0) + envs.view(view) * e.unsqueeze(0), dim=0)
 
     def double_haploid(self, population, n_offspring: int = 1) -> PackedPopulation:
         """`(n, m, 2)` -> `(n, n_offspring, m, 2)` (squeezed for one offspring); a batch `(E, n, m, 2)` is the

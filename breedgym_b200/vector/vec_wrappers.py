@@ -79,27 +79,23 @@ class SelectionScores(VectorWrapper):
 
     def _convert_actions_device(self, actions, random_key: np.ndarray) -> torch.Tensor:
         """The same translation on the GPU, batched over the envs: a stable descending sort (= top-k, ties -> lower
-        index), the library's permutation kernel for the random subset (env g uses keys[1 + g] of
-        split(random_key, total + 1): exactly the draw `VecBreedGym.reset` makes, `bg_reset_indices`), two gathers
-        and a repeat.  ~0.2 ms per step at 64 envs against 1.8 ms for the host version."""
+        index: `bg_topk`), the library's permutation kernel for the random subset (env g uses keys[1 + g] of
+        split(random_key, total + 1): exactly the draw `VecBreedGym.reset` makes, `bg_reset_indices`) and one kernel
+        for the pair lookup + repeat (`bg_diallel_pairs`): three launches, no host round trip."""
         sim, dev = self.simulator, self.device
         E, n, k, nc = self.num_envs, self.individual_per_gen, self.k, self.n_crosses
         begin, total = self.env.env_shard
         s = torch.as_tensor(actions, device=dev).to(torch.float32).reshape(E, n)  # jax computes in float32 as well
-        best = sim._top_k(s, k)                                                       # [E, k] (bg_topk: descending, ties -> lower index)
-        tri = getattr(self, "_triu_dev", None)
-        if tri is None or tri[0].device != dev:
-            ia, ib = np.triu_indices(k, k=1)
-            tri = self._triu_dev = (torch.from_numpy(ia).to(dev), torch.from_numpy(ib).to(dev))
-        n_pairs = tri[0].numel()
+        best = sim._top_k(s, k).to(torch.int32).contiguous()                          # [E, k] (bg_topk: descending, ties -> lower index)
+        n_pairs = k * (k - 1) // 2
         perm = torch.empty((E, nc), dtype=torch.int32, device=dev)
         key = np.ascontiguousarray(random_key, dtype=np.uint32)
         _lib.check(_lib.load().bg_reset_indices(sim._engine, _lib.nptr(key), total, begin, E, n_pairs, nc, sim._layout_id,
                                                 perm.data_ptr(), sim._stream()))
-        perm = perm.long()
-        chosen = torch.stack((torch.gather(best, 1, tri[0][perm]), torch.gather(best, 1, tri[1][perm])), dim=-1)  # [E, nc, 2]
-        out = chosen.repeat_interleave(int(ceil(n / nc)), dim=1)[:, :n]
-        return out.to(torch.int32).contiguous()
+        # chosen entries of the upper-triangular pair list, repeated ceil(n / nc) times, cut / padded to n: one kernel
+        out = torch.empty((E, n, 2), dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().bg_diallel_pairs(sim._engine, best.data_ptr(), perm.data_ptr(), E, k, nc, n, out.data_ptr(), sim._stream()))
+        return out
 
     def step(self, actions):
         begin, total = self.env.env_shard
@@ -131,8 +127,12 @@ def _pairs_from_scores(scores, n_crosses: int, device, sim: Optional[Simulator] 
         flat = flat.contiguous()
         vals = torch.empty((E, n_crosses), dtype=torch.float32, device=flat.device)
         idx32 = torch.empty((E, n_crosses), dtype=torch.int32, device=flat.device)
-        _lib.check(_lib.load().bg_topk(sim._engine, flat.data_ptr(), E, L, n_crosses, vals.data_ptr(), idx32.data_ptr(), sim._stream()))
-        idx = idx32.long()
+        lib = _lib.load()
+        _lib.check(lib.bg_topk(sim._engine, flat.data_ptr(), E, L, n_crosses, vals.data_ptr(), idx32.data_ptr(), sim._stream()))
+        # softmax -> counts -> prefix sums -> repeat -> (row, column): one kernel (`bg_pairs_from_topk`, csrc/pairs.cu)
+        pairs = torch.empty((E, n_crosses, 2), dtype=torch.int32, device=flat.device)
+        _lib.check(lib.bg_pairs_from_topk(sim._engine, vals.data_ptr(), idx32.data_ptr(), E, n_crosses, n, pairs.data_ptr(), sim._stream()))
+        return pairs
     else:
         # top-n_crosses with jax.lax.top_k's order (descending, ties -> lower flat index) WITHOUT sorting all n^2 scores:
         # 64-bit keys = (order-preserving integer image of the float32 score, inverted flat index) are unique, so a plain

@@ -185,6 +185,20 @@ int bg_reduce_mean(bg_engine *eng, const float *gebv, int64_t E, int64_t per_env
 int bg_topk(bg_engine *eng, const float *scores, int64_t rows, int64_t len, int32_t k, float *vals_out, int32_t *idx_out,
             void *stream);
 
+/* ---- pair selection after the top-k -----------------------------------------------
+ * PairScores._convert_actions (breedgym/vector/vec_wrappers.py:100-112; WheatBreedGym's conversion,
+ * breeding_programs_env.py:24-36): vals / idx = the k best flattened pair scores of every env (bg_topk's output,
+ * descending) -> pairs int32 [E][k][2]: pair b = (idx / row_len, idx % row_len) fills ceil(softmax(vals)[b] * k)
+ * output slots, `jnp.repeat(..., total_repeat_length=k)` (cut, or padded with the last pair).  k <= 1024. */
+int bg_pairs_from_topk(bg_engine *eng, const float *vals, const int32_t *idx, int64_t E, int32_t k, int64_t row_len,
+                       int32_t *pairs_out, void *stream);
+/* SelectionScores._convert_actions (vec_wrappers.py:60-78): best int32 [E][k] (the k best individuals, bg_topk) and
+ * perm int32 [E][nc] (the chosen entries of the C(k,2) upper-triangular pair list of `Simulator._diallel_indices`,
+ * = jax.random.choice(replace=False): bg_reset_indices) -> pairs int32 [E][n][2], every chosen pair repeated
+ * ceil(n / nc) times, `total_repeat_length=n`. */
+int bg_diallel_pairs(bg_engine *eng, const int32_t *best, const int32_t *perm, int64_t E, int32_t k, int32_t nc, int64_t n,
+                     int32_t *pairs_out, void *stream);
+
 /* ---- reset ------------------------------------------------------------------
  * VecBreedGym.reset's `_random_selection` (breedgym/vector/vec_env.py:22-27,
  * 120-128): env e draws permutation(keys[1+e], n_germ)[:n] where

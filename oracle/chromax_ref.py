@@ -182,6 +182,25 @@ def gebv_f32(pop: np.ndarray, effects: np.ndarray) -> np.ndarray:
     return gebv(pop, effects, dtype=np.float32).astype(np.float32)
 
 
+def gxe_effects(effects: np.ndarray, split_key, h2=None, layout="legacy") -> np.ndarray:
+    """chromax Simulator.__init__ (recalled): GxE marker effects = normal(split_key, (m, T)) rescaled so
+    that var(GxE) = (1 - h2) / h2 * var(GEBV) per trait (TraitModel.var = sum(effects^2) / 2); h2 defaults to 0.5."""
+    m, T = effects.shape
+    h2 = np.full(T, 0.5, dtype=np.float32) if h2 is None else np.asarray(h2, dtype=np.float32)
+    env = jp.normal(split_key, m * T, layout).reshape(m, T)
+    var_g = (np.sum(effects.astype(np.float32) ** 2, axis=0) / 2).astype(np.float32)
+    var_e = (np.sum(env ** 2, axis=0) / 2).astype(np.float32)
+    return (env * np.sqrt(((1 - h2) / h2 * var_g) / var_e).astype(np.float32)).astype(np.float32)
+
+
+def phenotype(pop: np.ndarray, effects: np.ndarray, gxe: np.ndarray, environments: np.ndarray, dtype=np.float64) -> np.ndarray:
+    """chromax `_phenotype`: mean over environments of GEBV(pop) + env * GxE(pop), GxE = TraitModel(gxe, offset=1)."""
+    g = gebv(pop, effects, dtype=dtype)
+    e = gebv(pop, gxe, offset=1.0, dtype=dtype)
+    envs = np.asarray(environments, dtype=dtype)
+    return np.mean(g[None] + envs.reshape(-1, *([1] * g.ndim)) * e[None], axis=0)
+
+
 def corrcoef(pop: np.ndarray) -> np.ndarray:
     """Simulator.corrcoef: correlation of each flattened individual with the mean."""
     pop = np.asarray(pop, dtype=bool)

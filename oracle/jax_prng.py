@@ -116,6 +116,32 @@ def uniform(k, n: int, layout: str = "legacy") -> np.ndarray:
     return bits_to_uniform(random_bits(k, n, layout))
 
 
+def erf_inv_f32(x: np.ndarray) -> np.ndarray:
+    """`lax.erf_inv` in float32 as XLA expands it (M. Giles, "Approximating the erfinv function": two degree-8
+    polynomials in w = -log1p(-x*x)); evaluated here in float32 Horner form."""
+    x = np.asarray(x, dtype=np.float32)
+    w = (-np.log1p((-x * x).astype(np.float32))).astype(np.float32)
+    lt = w < np.float32(5.0)
+    w = np.where(lt, w - np.float32(2.5), np.sqrt(w, dtype=np.float32) - np.float32(3.0)).astype(np.float32)
+    c_lt = [2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503, -0.00417768164,
+            0.246640727, 1.50140941]
+    c_ge = [-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613, 0.00943887047,
+            1.00167406, 2.83297682]
+    p = np.where(lt, np.float32(c_lt[0]), np.float32(c_ge[0])).astype(np.float32)
+    for a, b in zip(c_lt[1:], c_ge[1:]):
+        p = (np.where(lt, np.float32(a), np.float32(b)) + p * w).astype(np.float32)
+    out = (p * x).astype(np.float32)
+    return np.where(np.abs(x) == 1, np.copysign(np.float32(np.inf), x), out).astype(np.float32)
+
+
+def normal(k, n: int, layout: str = "legacy") -> np.ndarray:
+    """`jax.random.normal(key, (n,), float32)`: sqrt(2) * erf_inv(uniform(key, minval=nextafter(-1, 0), maxval=1))."""
+    lo = np.nextafter(np.float32(-1.0), np.float32(0.0))
+    f = bits_to_uniform(random_bits(k, n, layout))  # [0, 1)
+    u = np.maximum(lo, (f * (np.float32(1.0) - lo) + lo).astype(np.float32))
+    return (np.float32(np.sqrt(2)) * erf_inv_f32(u)).astype(np.float32)
+
+
 def shuffle_rounds(size: int) -> int:
     """Number of sort rounds in jax/_src/random.py `_shuffle`."""
     uint32max = np.iinfo(np.uint32).max

@@ -611,3 +611,101 @@ def test_topk_kernel_matches_lax_top_k_semantics(cuda_device, rows, length, k):
         rv, ri = jp.top_k(x[r] + np.float32(0.0), k)
         assert np.array_equal(idx[r].cpu().numpy(), ri), f"row {r}: indices differ from lax.top_k"
         assert np.array_equal(vals[r].cpu().numpy(), rv)
+
+
+@pytest.mark.parametrize("E,k,n", [(4, 60, 60), (3, 370, 370), (2, 1024, 1500), (5, 1, 9), (2, 7, 10)])
+def test_pairs_from_topk_kernel_matches_softmax_repeat(cuda_device, E, k, n):
+    """bg_pairs_from_topk (csrc/pairs.cu) == PairScores._convert_actions after the top-k (vec_wrappers.py:100-112):
+    ceil(softmax(values) * k) offspring per pair, `jnp.repeat(..., total_repeat_length=k)`, (flat // n, flat % n);
+    including a flat row (every pair once), one dominant pair (everything goes to it) and heavy ties."""
+    import torch
+
+    from breedgym_b200 import _lib
+    from breedgym_b200.simulator import Simulator
+
+    sim = Simulator(genetic_map=GMAP, device=0, seed=0)
+    rng = np.random.default_rng(E * 1000 + k)
+    vals = -np.sort(-rng.standard_normal((E, k)).astype(np.float32) * 3, axis=1)  # descending, as bg_topk returns them
+    vals[0] = 1.25                                                                  # flat: softmax = 1 / k exactly
+    if E > 1:
+        vals[1, 0] = vals[1, 0] + 60.0                                              # one pair takes every slot
+    if E > 2:
+        vals[2] = -np.sort(-np.round(vals[2]))                                      # ties
+    idx = np.stack([rng.permutation(n * n)[:k] for _ in range(E)]).astype(np.int32)
+    out = torch.empty((E, k, 2), dtype=torch.int32, device=cuda_device)
+    v_d, i_d = torch.from_numpy(vals).to(cuda_device), torch.from_numpy(idx).to(cuda_device)
+    _lib.check(_lib.load().bg_pairs_from_topk(sim._engine, v_d.data_ptr(), i_d.data_ptr(), E, k, n, out.data_ptr(), sim._stream()))
+    got = out.cpu().numpy()
+    for e in range(E):
+        ex = np.exp(vals[e] - vals[e].max())
+        sm = ex / ex.sum(dtype=np.float32)
+        reps = np.ceil(sm * np.float32(k)).astype(np.int32)
+        # (a count within one float32 ulp of an integer may round either way between exp implementations: compare the
+        #  slots whose owner does not depend on such a count)
+        safe = np.abs(sm.astype(np.float64) * k - np.round(sm.astype(np.float64) * k)) > 1e-4
+        ref = jp.repeat_total(np.stack((idx[e] // n, idx[e] % n), 1), reps, k)
+        if safe.all() or e == 0:
+            assert np.array_equal(got[e], ref), f"env {e}"
+        else:
+            assert (got[e] == ref).all(axis=1).mean() > 0.9
+    assert np.array_equal(got[0], np.stack((idx[0] // n, idx[0] % n), 1))           # flat row: every pair exactly once
+    if E > 1:
+        assert np.all(got[1] == np.array([idx[1, 0] // n, idx[1, 0] % n]))
+
+
+@pytest.mark.parametrize("E,k,nc,n", [(3, 10, 20, 200), (2, 5, 10, 7), (4, 30, 435, 500), (1, 2, 1, 4)])
+def test_diallel_pairs_kernel_matches_triu_repeat(cuda_device, E, k, nc, n):
+    """bg_diallel_pairs (csrc/pairs.cu) == SelectionScores._convert_actions after top-k and choice
+    (vec_wrappers.py:60-78): `_diallel_indices(best)[perm]`, each repeated ceil(n / nc) times, total_repeat_length n."""
+    import torch
+
+    from breedgym_b200 import _lib
+    from breedgym_b200.simulator import Simulator
+
+    sim = Simulator(genetic_map=GMAP, device=0, seed=0)
+    rng = np.random.default_rng(E + 10 * k)
+    best = np.stack([rng.permutation(1000)[:k] for _ in range(E)]).astype(np.int32)
+    n_pairs = k * (k - 1) // 2
+    perm = np.stack([rng.permutation(n_pairs)[:nc] for _ in range(E)]).astype(np.int32)
+    out = torch.empty((E, n, 2), dtype=torch.int32, device=cuda_device)
+    b_d, p_d = torch.from_numpy(best).to(cuda_device), torch.from_numpy(perm).to(cuda_device)
+    _lib.check(_lib.load().bg_diallel_pairs(sim._engine, b_d.data_ptr(), p_d.data_ptr(), E, k, nc, n, out.data_ptr(), sim._stream()))
+    got = out.cpu().numpy()
+    ia, ib = np.triu_indices(k, k=1)
+    rep = -(-n // nc)
+    for e in range(E):
+        chosen = np.stack([best[e][ia], best[e][ib]], axis=1)[perm[e]]
+        ref = jp.repeat_total(chosen, np.full(nc, rep, dtype=np.int32), n)
+        assert np.array_equal(got[e], ref), f"env {e}"
+
+
+def test_phenotype_gxe_matches_oracle(cuda_device):
+    """Simulator.phenotype / create_environments / GxE_model (chromax, scripts/time_wheat.py:17-50) against the oracle:
+    GxE effects from the constructor's split key, environments from the key chain, mean over environments of
+    GEBV + env * GxE in float64 (rtol 1e-5), and selection by `phenotype_index`."""
+    from breedgym_b200.simulator import Simulator
+    from breedgym_b200.utils.index_functions import phenotype_index
+
+    h2 = np.array([0.3], dtype=np.float32)
+    sim = Simulator(genetic_map=GMAP, trait_names=["Yield"], seed=11, device=0, h2=h2)
+    pop = np.load(GENOME)[:64]
+    key0 = jp.key(11)
+    halves = jp.split(key0, 2)
+    gxe = cr.gxe_effects(sim.GEBV_model.marker_effects, halves[1], h2)
+    assert np.array_equal(sim.GxE_model.marker_effects, gxe)
+    nxt = jp.split(halves[0], 2)                       # create_environments: random_key, k = split(random_key)
+    envs = sim.create_environments(5)
+    assert np.array_equal(envs, jp.normal(nxt[1], 5))
+    assert np.array_equal(sim.random_key, nxt[0])
+    got = sim.phenotype(pop, environments=envs).cpu().numpy()
+    ref = cr.phenotype(pop, sim.GEBV_model.marker_effects, gxe, envs)
+    assert got.shape == (64, 1) and np.allclose(got, ref, rtol=RTOL, atol=1e-4 * np.abs(ref).max())
+    with pytest.raises(ValueError):
+        sim.phenotype(pop, num_environments=2, environments=envs)
+    one = sim.phenotype(pop)                            # draws one environment from the key chain
+    e1 = jp.normal(jp.split(nxt[0], 2)[1], 1)
+    assert np.allclose(one.cpu().numpy(), cr.phenotype(pop, sim.GEBV_model.marker_effects, gxe, e1), rtol=RTOL,
+                       atol=1e-4 * np.abs(ref).max())
+    sel, idx = sim.select(pop, 7, phenotype_index(sim, envs))
+    assert np.array_equal(idx, jp.top_k(got[:, 0], 7)[1])
+    assert np.array_equal(np.asarray(sel), pop[idx])

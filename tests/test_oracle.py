@@ -36,6 +36,32 @@ def test_jax_documented_values_legacy():
     assert np.float32(jp.uniform(jp.key(0), 1, "legacy")[0]) == np.float32(0.41845703)
 
 
+def test_jax_documented_normal_vector_legacy():
+    """`jax.random.normal(PRNGKey(0), (10,))` as the JAX quickstart prints it (jax <= 0.4, the layout this repo
+    defaults to), and `normal(PRNGKey(0), (1,))` from the jax.random docs: pins Threefry, the counter layout of
+    `random_bits`, the bits -> uniform(-1, 1) map and XLA's float32 erf_inv expansion in one go."""
+    doc = np.array([-0.3721109, 0.26423115, -0.18252768, -0.7368197, -0.44030377, -0.1521442, -0.67135346, -0.5908641,
+                    0.73168886, 0.5673026], dtype=np.float32)
+    assert np.array_equal(jp.normal(jp.key(0), 10, "legacy"), doc)
+    assert jp.normal(jp.key(0), 1, "legacy")[0] == np.float32(-0.20584226)
+
+
+def test_host_normal_equals_oracle_normal():
+    from breedgym_b200 import _lib, jaxlike
+
+    for lay in ("legacy", "partitionable"):
+        for n in (1, 2, 7, 1000, 4097):
+            assert np.array_equal(jaxlike.normal(_lib.key_data(5), n, lay), jp.normal(jp.key(5), n, lay))
+
+
+def test_gxe_effects_have_the_target_variance():
+    eff = np.random.default_rng(0).standard_normal((500, 3)).astype(np.float32)
+    h2 = np.array([0.5, 0.25, 0.8], dtype=np.float32)
+    gxe = cr.gxe_effects(eff, jp.split(jp.key(3), 2)[1], h2)
+    want = (1 - h2) / h2 * (eff**2).sum(0) / 2
+    assert np.allclose((gxe**2).sum(0) / 2, want, rtol=1e-5)
+
+
 def test_jax_documented_values_partitionable():
     assert jp.split(jp.key(0), 2, "partitionable").tolist() == [[1797259609, 2579123966], [928981903, 3453687069]]
     assert abs(float(jp.uniform(jp.key(0), 1, "partitionable")[0]) - 0.947667) < 1e-6
