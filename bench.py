@@ -290,6 +290,19 @@ class Harness:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
+    def align_start(self):
+        """Ranks leave an NCCL barrier tens of microseconds apart, and a rank that starts late makes every other rank's
+        closing event (which waits for ALL ranks' rewards) that much later: after the barrier the ranks agree on a
+        common wall-clock deadline (same host, same clock) and spin until it."""
+        if self.world == 1:
+            return
+        t = self.torch.tensor([time.time_ns() + 400_000], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        deadline = int(t.item())
+        self.torch.cuda.synchronize()
+        while time.time_ns() < deadline:
+            pass
+
     def max_over_ranks(self, x):
         if self.world == 1:
             return x
@@ -309,6 +322,7 @@ class Harness:
         stream = torch.cuda.current_stream(self.dev)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
+        self.align_start()
         start.record(stream)
         t0 = time.perf_counter()
         for i in range(steps):
