@@ -32,7 +32,7 @@ def main():
             name = re.sub(r"\(anonymous namespace\)::", "", name)
             cur = kernels.setdefault(name.split("(")[0], collections.Counter())
             continue
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
         if m and cur is not None:
             cur[m.group(1)] += 1
     print(f"# {LIB.name}: cubin architectures {archs}; instruction counts per kernel (static SASS)")
