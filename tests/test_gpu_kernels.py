@@ -461,18 +461,22 @@ def test_fused_cross_gebv_equals_cross_then_gebv(cuda_device, m, T, E, n_src, n)
     a = torch.from_numpy(acts).to(cuda_device)
     import os
 
-    # default: the single fused kernel; engine option fuse=0: blend + GEBV kernels
-    for no_fuse in (False, True):
+    # the fused step kernel with one CTA per (tile, K range) (fused_dyn=0), the persistent one with the dynamic work
+    # queue (fused_dyn=1: the kernel launches with many tiles take), and blend + GEBV kernels (fuse=0)
+    for fuse, dyn in ((1, 0), (1, 1), (0, 0)):
         out.zero_()
         gebv.zero_()
-        sim.set_option("fuse", 0 if no_fuse else 1)
+        sim.set_option("fuse", fuse)
+        sim.set_option("fused_dyn", dyn)
         try:
-            _lib.check(_lib.load().bg_cross_gebv(sim._engine, packed.words.data_ptr(), a.data_ptr(), out.data_ptr(), E, n_src, n,
-                                                 _lib.nptr(key), sim._layout(), sim._schedule(), gebv.data_ptr(), sim._stream()))
+            for _ in range(2):  # twice: the persistent kernel's work counter must come back to zero
+                _lib.check(_lib.load().bg_cross_gebv(sim._engine, packed.words.data_ptr(), a.data_ptr(), out.data_ptr(), E, n_src, n,
+                                                     _lib.nptr(key), sim._layout(), sim._schedule(), gebv.data_ptr(), sim._stream()))
         finally:
             sim.set_option("fuse", 1)
-        assert np.array_equal(out.cpu().numpy(), ref_pop.words.cpu().numpy())
-        assert np.array_equal(gebv.cpu().numpy(), ref_gebv)
+            sim.set_option("fused_dyn", -1)
+        assert np.array_equal(out.cpu().numpy(), ref_pop.words.cpu().numpy()), (fuse, dyn)
+        assert np.array_equal(gebv.cpu().numpy(), ref_gebv), (fuse, dyn)
     oref = co.cross_envs(pops, cr.normalize_index(acts, n_src), sim.recombination_vec, key)
     from breedgym_b200.population import PackedPopulation
 
@@ -558,19 +562,21 @@ def test_fused_step_kernel_full_size_equals_two_kernel_path(cuda_device, m, T, E
     acts = torch.randint(0, n, (E, n, 2), dtype=torch.int32, device=cuda_device, generator=g)
     key = jp.key(99)
     outs, gebvs = [], []
-    for no_fuse in (False, True):
+    for fuse, dyn in ((1, 0), (0, 0), (1, 1)):  # one CTA per (tile, K range); blend + GEBV; persistent with the work queue
         out = torch.zeros((E, n, 2, W), dtype=torch.int32, device=cuda_device)
         gebv = torch.zeros((E, n, T), dtype=torch.float32, device=cuda_device)
-        sim.set_option("fuse", 0 if no_fuse else 1)
+        sim.set_option("fuse", fuse)
+        sim.set_option("fused_dyn", dyn)
         try:
             _lib.check(_lib.load().bg_cross_gebv(sim._engine, pop.data_ptr(), acts.data_ptr(), out.data_ptr(), E, n, n,
                                                  _lib.nptr(key), sim._layout(), sim._schedule(), gebv.data_ptr(), sim._stream()))
         finally:
             sim.set_option("fuse", 1)
+            sim.set_option("fused_dyn", -1)
         outs.append(out)
         gebvs.append(gebv)
-    assert torch.equal(outs[0], outs[1])
-    assert torch.equal(gebvs[0], gebvs[1])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.equal(gebvs[0], gebvs[1]) and torch.equal(gebvs[0], gebvs[2])
     # allele provenance on one env: offspring plane p only holds bits present in one of parent p's two planes
     e = E // 3
     par = pop[e][acts[e].long()]  # [n, 2 (which parent), 2 (plane), W]
