@@ -46,6 +46,41 @@ def test_jax_documented_normal_vector_legacy():
     assert jp.normal(jp.key(0), 1, "legacy")[0] == np.float32(-0.20584226)
 
 
+def test_jax_documented_split_chain_legacy():
+    """The key chain the JAX "Common gotchas" notebook prints (PRNGKey(0), two rounds of `key, subkey = split(key)`,
+    `normal(subkey, (1,))`): the chain `Simulator.cross` walks, from documentation that predates this repo."""
+    k = jp.key(0)
+    k, sub = jp.split(k, 2, "legacy")
+    assert k.tolist() == [4146024105, 967050713] and sub.tolist() == [2718843009, 1272950319]
+    assert jp.normal(sub, 1, "legacy")[0] == np.float32(-1.2515389)
+    k, sub = jp.split(k, 2, "legacy")
+    assert k.tolist() == [2384771982, 3928867769] and sub.tolist() == [1278412471, 2182328957]
+    assert jp.normal(sub, 1, "legacy")[0] == np.float32(-0.58665055)
+    # the library's host-side chain (bg_key_chain_next: what bg_vec_step advances) walks the same keys
+    from breedgym_b200 import _lib
+
+    state = _lib.key_data(0).copy()
+    out = np.zeros(6, dtype=np.uint32)
+    _lib.check(_lib.load().bg_key_chain_next(_lib.nptr(state), 0, _lib.nptr(out)))
+    assert state.tolist() == [4146024105, 967050713] and out[:2].tolist() == [2718843009, 1272950319]
+    _lib.check(_lib.load().bg_key_chain_next(_lib.nptr(state), 0, _lib.nptr(out)))
+    assert state.tolist() == [2384771982, 3928867769] and out[:2].tolist() == [1278412471, 2182328957]
+
+
+def test_jax_documented_multiway_split_and_vector_draws_legacy():
+    """More values from "JAX - The Sharp Bits": `key, *subkeys = split(key, 4)` on the chain's third key and one normal
+    per subkey; `normal(PRNGKey(42), (3,))` against the three draws from `split(PRNGKey(42), 3)` (the notebook's
+    "no sequential equivalence" example).  Pins `split(num > 2)` and odd-length `random_bits` in the legacy layout."""
+    k = np.array([2384771982, 3928867769], dtype=np.uint32)
+    subs = jp.split(k, 4, "legacy")[1:]
+    got = [jp.normal(x, 1, "legacy")[0] for x in subs]
+    assert got == [np.float32(-0.37533438), np.float32(0.98645043), np.float32(0.14553197)]
+    assert np.array_equal(jp.normal(jp.key(42), 3, "legacy"), np.array([0.18693547, -1.2806505, -1.5593132], dtype=np.float32))
+    each = [jp.normal(x, 1, "legacy")[0] for x in jp.split(jp.key(42), 3, "legacy")]
+    # (the notebook prints these three inside one array, i.e. rounded to 8 significant digits)
+    assert np.allclose(each, [-0.04838832, 0.10796154, -1.2226542], rtol=2e-7, atol=0)
+
+
 def test_host_normal_equals_oracle_normal():
     from breedgym_b200 import _lib, jaxlike
 
