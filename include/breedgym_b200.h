@@ -83,6 +83,11 @@ int bg_engine_destroy(bg_engine *eng);
 /* Tuning / cross-check switches (none changes results).  bg_engine_create reads each once from the
  * environment as BG_OPT_<NAME>; nothing on the step path calls getenv.
  *   fuse (1)            0: bg_cross_gebv / bg_vec_step run blend + GEBV kernels instead of the fused one
+ *   fused_dyn (-1)      which fused step kernel: 0 = one CTA per (tile, K range), 1 = persistent CTAs with a dynamic
+ *                       work queue, -1 = the latter from 4 tiles per resident CTA on (512 envs x 370 per GPU)
+ *   xg_parts (0)        the persistent kernel's split of a tile's K range, proportions as decimal digits
+ *                       (8642 = 8 : 6 : 4 : 2); 0 = by tiles per CTA
+ *   step_pdl (1)        programmatic dependent launch of consecutive step kernels (prologue overlaps the previous tail)
  *   gebv_algo (0)       default algorithm of bg_gebv, see bg_gebv_algo
  *   gebv_digits (0)     base-256 digits of the tensor-core GEBV operand: 0 = as many as the map needs,
  *                       4..8 fixed (set BEFORE bg_engine_set_map)
@@ -234,7 +239,8 @@ int bg_vec_reset_adopt(bg_engine *eng, void *stream);
  * pageable; NULL = the actions are already in actions_dev) to `actions_dev`,
  * advances the simulator's key chain IN PLACE (`key_state`: host uint32[2] =
  * Simulator.random_key; chromax: `random_key, k = split(random_key)`), runs
- * cross -> GEBV (-> max reward when reward_dev is non-NULL), copies gebv/reward
+ * cross -> GEBV (-> max reward when reward_dev is non-NULL; with a peer exchange attached to the engine,
+ * bg_engine_set_peer, the same reduction also stores the rewards into every rank's window), copies gebv/reward
  * back to the host buffers when non-NULL, and synchronises the stream iff any
  * device->host copy was requested.  The crossover masks depend on the key chain
  * only: the masks of the following steps (option `lookahead`) are generated by
