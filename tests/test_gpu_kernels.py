@@ -584,3 +584,15 @@ def test_fused_step_kernel_full_size_equals_two_kernel_path(cuda_device, m, T, E
     for p in range(2):
         c, h0, h1 = child[:, p], par[:, p, 0], par[:, p, 1]
         assert bool(torch.all((c & ~(h0 | h1)) == 0)) and bool(torch.all((~c & (h0 & h1)) == 0))
+
+
+def test_fuzz_fused_step_kernels(cuda_device):
+    """scripts/fuzz_fused.py: randomised shapes (1 ... 100 002 markers, 1 ... 24 traits, 2 ... 200 envs, ragged tiles, index wrap /
+    clamp, both PRNG layouts) -- both fused step kernels == the blend + GEBV kernels, bit for bit."""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("fuzz_fused", Path(__file__).resolve().parents[1] / "scripts" / "fuzz_fused.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run_cases(12, 20261018, verbose=False) == 0
