@@ -70,7 +70,10 @@ def config_dict(n_gpus, replicas=REPLICAS, envs_per_gpu=None, envs_total=None):
         "parallelism": f"env-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
         "l2": f"inputs larger than L2: {replicas} independent replicas stepped round-robin "
               f"({replicas} x {2 * epg * N_IND * 2560 / 1e6:.0f} MB of populations between reuse, L2 = 126 MB); "
-              f"per-kernel breakdown: 256 MiB flush",
+              f"step kernel: back to back over the replicas' populations, other kernels behind a 256 MiB flush",
+        "window": "the replicas are staggered (episode ends and mask batches spread over the round-robin); the closing event of "
+                  "the timed region waits for everything the steps started on the library's side stream (bg_engine_join: masks "
+                  "of following steps, prefetched resets) and for the reward exchange",
         "observation": "packed bit planes resident in HBM (bool observation materialised on request only)",
         "rng": "threefry2x32 legacy layout, key schedule S2, seed 7",
         "stream": "steps on a CUDA stream of priority -1 (torch.cuda.Stream(priority=-1)); the library's mask lookahead runs on its own side stream at priority 0",
@@ -346,13 +349,21 @@ def vec_value_leg(h, make_env, acts_dev, K, W, replicas, sample_clocks=None, ste
         envs[i % replicas].step(acts_dev[i % n_act])
 
     def finish():
-        # env-sharded runs exchange the rewards asynchronously (async_rewards): the closing event waits for every
-        # rank's rewards of every replica's last episode, so the timed region carries the whole exchange
+        # The closing event waits for everything the timed steps STARTED: the crossover masks of following steps that
+        # the library generates on its side stream, prefetched resets (env.join = bg_engine_join), and -- env-sharded
+        # runs exchange the rewards asynchronously -- every rank's rewards of every replica's last episode.
         for env in envs:
+            env.join()
             if hasattr(env, "wait_rewards"):
                 env.wait_rewards()
 
     h.spin_up()
+    # Stagger the replicas: replica r runs a few steps ahead, so that the replicas' episode ends (every 10th step) and
+    # mask batches (every 8th) are spread over the round-robin the way independent env sets are in a long run -- not
+    # all on consecutive iterations, which puts either all or none of them inside a K = 20 window.
+    for r in range(replicas):
+        for j in range(r * NUM_GENERATIONS // replicas):  # 0, 2, 5, 7 at 4 replicas
+            envs[r].step(acts_dev[j % n_act])
     for i in range(max(W, replicas * (NUM_GENERATIONS + 1))):
         step(i)
     h.timed(step, K, finish)
@@ -562,10 +573,17 @@ def run_ours(args):
     def host_step(i):
         envs_h[i % replicas].step(acts_host[i % 16])
 
+    def host_finish():  # as in the device-resident leg: the closing event waits for what the steps started on side streams
+        for env in envs_h:
+            env.join()
+
     h.spin_up()
+    for r in range(replicas):  # staggered like the device-resident leg
+        for j in range(r * NUM_GENERATIONS // replicas):
+            envs_h[r].step(acts_host[j % 16])
     for i in range(max(W, replicas * (NUM_GENERATIONS + 1))):
         host_step(i)
-    h.timed(host_step, min(K, 500))  # untimed rehearsal, as above
+    h.timed(host_step, min(K, 500), host_finish)  # untimed rehearsal, as above
     # timed in blocks (same total K): a block far slower than the others points at the box (clock state, a descheduled
     # host thread), not at the path; reported beside the total
     nblk = 4 if K >= 400 else 1
@@ -575,7 +593,7 @@ def run_ours(args):
     base = 0
     for b in range(nblk):
         kb = K // nblk + (1 if b < K % nblk else 0)
-        blocks.append(h.timed(lambda i, base=base: host_step(base + i), kb)[0] / kb)
+        blocks.append(h.timed(lambda i, base=base: host_step(base + i), kb, host_finish)[0] / kb)
         base += kb
     clocks_e2e = sampler_e2e.stop()
     t_e2e = h.max_over_ranks(sum(bt * (K // nblk + (1 if b < K % nblk else 0)) for b, bt in enumerate(blocks)))

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "bg_vec_reset_prefetch": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
     "bg_vec_reset_adopt": (c_int, [c_void_p, c_void_p]),
+    "bg_engine_join": (c_int, [c_void_p, c_void_p]),
     "bg_vec_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bg_engine_set_option": (c_int, [c_void_p, c_char_p, c_int64]),

@@ -279,6 +279,7 @@ int bg_engine_destroy(bg_engine *eng)
         }
         if (eng->tmp_event) cudaEventDestroy(eng->tmp_event);
         if (eng->reset_ready) cudaEventDestroy(eng->reset_ready);
+        if (eng->join_event) cudaEventDestroy(eng->join_event);
         cudaFree(eng->d_mut);
         cudaFree(eng->d_acc);
         cudaFree(eng->d_xg_work);
@@ -824,6 +825,16 @@ int bg_vec_reset_prefetch(bg_engine *eng, const uint32_t *germplasm, int64_t n_g
     if (rc) return rc;
     BG_CUDA(cudaEventRecord(eng->reset_ready, eng->side));
     eng->reset_pending = true;
+    return BG_OK;
+}
+
+int bg_engine_join(bg_engine *eng, void *stream)
+{
+    BG_ENTER(eng);
+    if (!eng->side) return BG_OK;
+    if (!eng->join_event) BG_CUDA(cudaEventCreateWithFlags(&eng->join_event, cudaEventDisableTiming));
+    BG_CUDA(cudaEventRecord(eng->join_event, eng->side));
+    BG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, eng->join_event, 0));
     return BG_OK;
 }
 

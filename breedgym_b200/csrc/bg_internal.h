@@ -85,6 +85,7 @@ struct bg_engine {
     cudaStream_t side = nullptr;        // lookahead stream
     cudaEvent_t tmp_event = nullptr;
     cudaEvent_t reset_ready = nullptr;  // recorded behind a prefetched reset on the side stream
+    cudaEvent_t join_event = nullptr;   // bg_engine_join
     bool reset_pending = false;
     uint32_t *d_mut = nullptr;          // mutation scratch of bg_meiosis_masks
     size_t mut_cap = 0;                 // words

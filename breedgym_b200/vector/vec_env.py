@@ -462,6 +462,13 @@ class VecBreedGym(VectorEnv):
             _lib.check(rc)
         pre["key"], pre["pending"] = key, True
 
+    def join(self):
+        """Order the current stream behind the work this env's engine runs on its own side stream (the crossover masks
+        of the following steps, the prefetched reset): `bg_engine_join`.  For timing harnesses."""
+        rc = _lib.load().bg_engine_join(self.simulator._engine, self._raw_stream(self._dev_index))
+        if rc:
+            _lib.check(rc)
+
     def get_info(self) -> dict:
         gebv = self.simulator.GEBV_model(self.populations)
         return {"GEBV": gebv.cpu().numpy() if self.info_device == "host" else gebv}

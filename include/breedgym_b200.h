@@ -232,6 +232,10 @@ int bg_vec_reset_prefetch(bg_engine *eng, const uint32_t *germplasm, int64_t n_g
                           int64_t E_total, int64_t env_begin, int64_t E, int64_t n, int layout, int32_t *idx_dev,
                           uint32_t *pop_out, float *gebv_dev, const float *germ_gebv, void *stream);
 int bg_vec_reset_adopt(bg_engine *eng, void *stream);
+/* Order `stream` behind everything the engine has enqueued so far on its internal side stream (the crossover masks of
+ * FOLLOWING steps, a prefetched reset): a timing harness calls it before its closing event so that a measured window
+ * pays for all the work its steps started, not only for what the step stream itself ran. */
+int bg_engine_join(bg_engine *eng, void *stream);
 
 /* ---- one-call vector-env step ------------------------------------------------
  * VecBreedGym.step hot path (breedgym/vector/vec_env.py:88-100) with host
