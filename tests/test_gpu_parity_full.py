@@ -26,17 +26,20 @@ def gym():
     return gym_compat
 
 
-@pytest.mark.parametrize("E", [64, 512])
-def test_fused_step_kernel_every_row_equals_c_oracle(cuda_device, E):
-    """BASELINE C2 (64 envs x 370 x 10 000) and one GPU's share of C5 (512 envs): the fused cross + GEBV kernel,
-    called through bg_cross_gebv, against the C oracle on EVERY offspring row and every GEBV (the oracle draws the 2n
-    masks once and is run per 64-env chunk with the same key, so the host never holds more than one chunk)."""
+@pytest.mark.parametrize("E,fused_dyn", [(64, 0), (64, 1), (512, 0), (512, 1)])
+def test_fused_step_kernel_every_row_equals_c_oracle(cuda_device, E, fused_dyn):
+    """BASELINE C2 (64 envs x 370 x 10 000) and one GPU's share of C5 (512 envs): BOTH fused cross + GEBV kernels (one
+    CTA per (tile, K range); persistent with the dynamic work queue -- the library's own choice is the former at 64 envs
+    and the latter at 512), called through bg_cross_gebv, against the C oracle on EVERY offspring row and every GEBV
+    (the oracle draws the 2n masks once and is run per 64-env chunk with the same key, so the host never holds more
+    than one chunk)."""
     import torch
 
     from breedgym_b200 import _lib
     from breedgym_b200.simulator import Simulator
 
-    sim = Simulator(genetic_map=DATA / "small_genetic_map.txt", trait_names=["Yield"], device=0, seed=0)
+    sim = Simulator(genetic_map=DATA / "small_genetic_map.txt", trait_names=["Yield"], device=0, seed=0,
+                    engine_options={"fused_dyn": fused_dyn})
     N, m, CH = 370, sim.n_markers, 64
     rng = np.random.default_rng(E)
     acts = rng.integers(0, N, (E, N, 2)).astype(np.int32)
