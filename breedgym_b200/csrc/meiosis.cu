@@ -225,6 +225,10 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : (NT_MAX == 512 ? 2
 {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t wtot[32];
+    __shared__ uint32_t row_keys[4];  // (rec, mut) keys of the row in progress
+    // a dependent kernel launched with programmatic stream serialization (the GEBV of these offspring, gebv_tc2.cu) may
+    // run its prologue while this grid drains; kernels launched the ordinary way are not affected
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     uint32_t *S = smem;
     uint32_t *Mu = smem + (P.Wpad + 8);
     const uint32_t tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
@@ -239,16 +243,27 @@ __global__ void __launch_bounds__(NT_MAX, NT_MAX == 256 ? 4 : (NT_MAX == 512 ? 2
         S[i] = 0;
         if (has_mut) Mu[i] = 0;
     }
-    // per-gamete key: #q of split(k, rows); S2 splits it again into (rec, mut)
-    const uint32_t ki = P.same_key ? 0u : kb;
-    const TfKey kc = tf_make_key(P.keys[ki][0], P.keys[ki][1]);
-    const TfKey kq = tf_split_at(kc, q, P.rows, LAYOUT);
-    TfKey krec = kq, kmut = kq;
-    if (P.schedule == BG_SCHEDULE_S2) {
-        krec = tf_split_at(kq, 0, 2, LAYOUT);
-        if (has_mut) kmut = tf_split_at(kq, 1, 2, LAYOUT);
+    // per-gamete key: #q of split(k, rows); S2 splits it again into (rec, mut).  Two or three Threefry blocks that
+    // every warp used to repeat (a warp instruction costs the same for 1 or 32 lanes, so the redundancy across WARPS
+    // is what costs): warp 0 derives them, the others pick them up behind the barrier that follows the zero fill.
+    if (warp == 0) {
+        const uint32_t ki = P.same_key ? 0u : kb;
+        const TfKey kc = tf_make_key(P.keys[ki][0], P.keys[ki][1]);
+        const TfKey kq = tf_split_at(kc, q, P.rows, LAYOUT);
+        TfKey kr = kq, km = kq;
+        if (P.schedule == BG_SCHEDULE_S2) {
+            kr = tf_split_at(kq, 0, 2, LAYOUT);
+            if (has_mut) km = tf_split_at(kq, 1, 2, LAYOUT);
+        }
+        if (lane == 0) {
+            row_keys[0] = kr.k0;
+            row_keys[1] = kr.k1;
+            row_keys[2] = km.k0;
+            row_keys[3] = km.k1;
+        }
     }
     __syncthreads();
+    const TfKey krec = tf_make_key(row_keys[0], row_keys[1]), kmut = tf_make_key(row_keys[2], row_keys[3]);
 
 #if defined(BG_FAKE_CONST_THR)   // timing experiment only (wrong masks): what do the threshold loads cost beside the step kernel?
     draw_bits<LAYOUT, true>(S, krec, nullptr, nullptr, 12000u, m, lane, warp, NW, P.one);
