@@ -427,7 +427,8 @@ def run_ours(args):
     def actions(count, n_act, seed):
         rng = np.random.default_rng(seed)
         host = [rng.integers(0, N_IND, (count, N_IND, 2), dtype=np.int32) for _ in range(n_act)]
-        return host, [torch.from_numpy(a).to(dev) for a in host]
+        # host copies live in pinned memory (the e2e leg's inputs: the step copies them to the device as they are)
+        return [torch.from_numpy(a).pin_memory() for a in host], [torch.from_numpy(a).to(dev) for a in host]
 
     total_envs = ENVS_PER_GPU * world
     begin, count = shard_range(total_envs, world, rank)
@@ -655,7 +656,7 @@ def run_ours(args):
                         "generation (Threefry, integer-issue bound) that runs beside the step kernels"},
             "clocks": clocks,
             "e2e": {"value": total_envs * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "VecBreedGym.step(numpy actions) -> numpy GEBV / rewards, one sync per step",
+                    "api": "VecBreedGym.step(int32 actions in pinned host memory) -> numpy GEBV / rewards, one sync per step",
                     "us_per_step_by_block": [round(1e6 * bt, 1) for bt in blocks], "clocks": clocks_e2e},
             "gpu_launches": int(launches),
             "gpu_launches_note": f"our kernels in {K} steps (counted over a repeat of the timed loop; "

@@ -261,6 +261,17 @@ class VecBreedGym(VectorEnv):
             shape = tuple(actions.shape)
             act_host_ptr, act_dev_ptr = None, actions.data_ptr()
             io = None
+        elif (actions.__class__ is torch.Tensor and actions.dtype == torch.int32 and actions.is_contiguous()
+              and actions.is_pinned()):
+            # a pinned host tensor goes to the device as it is: no staging copy (the asynchronous H2D reads it, so in
+            # device mode the caller keeps it unchanged until the step has run; host mode synchronises anyway)
+            shape = tuple(actions.shape)
+            io = self._io
+            if io is None or io["shape"] != shape:
+                if len(shape) != 3 or shape[0] != E or shape[2] != 2:
+                    raise ValueError(f"actions must have shape ({E}, n, 2), got {shape}")
+                io = self._host_io(shape, T)
+            act_host_ptr, act_dev_ptr = actions.data_ptr(), io["act_dev"]
         else:
             a = np.asarray(actions)
             shape = a.shape

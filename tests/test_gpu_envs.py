@@ -709,3 +709,30 @@ def test_phenotype_gxe_matches_oracle(cuda_device):
     sel, idx = sim.select(pop, 7, phenotype_index(sim, envs))
     assert np.array_equal(idx, jp.top_k(got[:, 0], 7)[1])
     assert np.array_equal(np.asarray(sel), pop[idx])
+
+
+def test_pinned_host_actions_equal_numpy_actions(cuda_device):
+    """A pinned int32 host tensor is copied to the device as it is (no staging copy): same trajectory as numpy actions,
+    in host and in device mode."""
+    import torch
+
+    from breedgym_b200.vector import VecBreedGym
+
+    n = 40
+    for mode in ("host", "device"):
+        kw = dict(num_envs=3, initial_population=GENOME, genetic_map=GMAP, individual_per_gen=n, num_generations=3, info_device=mode)
+        a, b = VecBreedGym(**kw), VecBreedGym(**kw)
+        a.reset(seed=4)
+        b.reset(seed=4)
+        rng = np.random.default_rng(1)
+        for _ in range(5):
+            act = rng.integers(0, n, (3, n, 2)).astype(np.int32)
+            pa, ra, _, ta, ia = a.step(act)
+            pinned = torch.from_numpy(act.copy()).pin_memory()
+            pb, rb, _, tb, ib = b.step(pinned)
+            torch.cuda.synchronize()
+            assert np.array_equal(np.asarray(pa), np.asarray(pb))
+            ga, gb = ia["GEBV"], ib["GEBV"]
+            assert np.array_equal(ga.cpu().numpy() if hasattr(ga, "cpu") else ga, gb.cpu().numpy() if hasattr(gb, "cpu") else gb)
+            assert np.array_equal(ra.cpu().numpy() if hasattr(ra, "cpu") else ra, rb.cpu().numpy() if hasattr(rb, "cpu") else rb)
+            assert np.array_equal(ta, tb)
